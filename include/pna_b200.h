@@ -1,0 +1,182 @@
+/*
+ * pna_b200.h -- C ABI of libpna_sm100.so, the B200 (sm_100a) PNA aggregation path.
+ *
+ * This is the drop-in boundary for ONE hot path of lukecavabarrett/pna: the
+ * neighbourhood aggregation of the PNA layer (gather of source features, the
+ * simultaneous mean/max/min/std(/sum/var) aggregators, the degree scalers, the
+ * concatenated [N, S*A*F] result).  Plain pointers and sizes only; every buffer
+ * is owned by the caller (PyTorch in this repo); all pointers are DEVICE pointers
+ * unless stated otherwise; every call enqueues on the caller's stream.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   models/pytorch_geometric/pna.py:152-159, :242-249   PNAConv(.Simple).aggregate
+ *   models/pytorch_geometric/aggregators.py:9-32        scatter sum/mean/min/max/var/std
+ *   models/pytorch_geometric/scalers.py:8-29            identity/amplification/attenuation/linear/inverse_linear
+ *   models/dgl/pna_layer.py:45-50, :189-194             PNATower.reduce_func / PNASimpleLayer.reduce_func
+ *   models/dgl/aggregators.py:6-26, models/dgl/scalers.py:8-19
+ *   torch_geometric MessagePassing.propagate gather of x_j (pna.py:129, :236)
+ *
+ * Return value of every int function: 0 = ok, negative = pna_status.
+ * pna_last_error() gives a thread-local human-readable message for the last failure.
+ */
+#ifndef PNA_B200_H
+#define PNA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNA_ABI_VERSION 3
+
+typedef void* pna_stream_t; /* a cudaStream_t / CUstream, passed opaquely */
+
+enum pna_status {
+  PNA_OK = 0,
+  PNA_ERR_BAD_ARG = -1,     /* null pointer, negative size, inconsistent descriptor */
+  PNA_ERR_UNSUPPORTED = -2, /* dtype / size outside what the kernels take (e.g. E >= 2^31) */
+  PNA_ERR_CUDA = -3,        /* a CUDA runtime call failed; message carries cudaGetErrorString */
+  PNA_ERR_INDEX = -4,       /* an edge endpoint outside [0, n_nodes) was found while building the CSR */
+  PNA_ERR_WORKSPACE = -5    /* caller-provided workspace / capacity too small */
+};
+
+enum pna_dtype { PNA_F32 = 0, PNA_BF16 = 1 };
+
+/* Aggregator codes (order of appearance in the layer's ctor list fixes the column layout,
+ * pna.py:70,153-154).  Packed 4 bits each, first aggregator in the low nibble. */
+enum pna_aggr { PNA_AGGR_SUM = 0, PNA_AGGR_MEAN = 1, PNA_AGGR_MIN = 2, PNA_AGGR_MAX = 3, PNA_AGGR_VAR = 4, PNA_AGGR_STD = 5 };
+/* Scaler codes (scalers.py:32-38), packed the same way. */
+enum pna_scaler { PNA_SCALE_IDENTITY = 0, PNA_SCALE_AMPLIFICATION = 1, PNA_SCALE_ATTENUATION = 2, PNA_SCALE_LINEAR = 3, PNA_SCALE_INVERSE_LINEAR = 4 };
+
+#define PNA_MAX_AGGR 6
+#define PNA_MAX_SCALERS 5
+
+enum pna_flags {
+  PNA_FLAG_ZERO_ISOLATED = 1u, /* DGL semantics: a node with no in-edge is never reduced, all its S*A*F columns are 0
+                                  (models/dgl/pna_layer.py:64 update_all).  Default (PyG/torch_scatter semantics):
+                                  mean=min=max=0, std=sqrt(1e-5), then scaled. */
+  PNA_FLAG_SKIP_LIGHT = 2u,    /* do not process rows below the split threshold (used to overlap halo exchange) */
+  PNA_FLAG_SKIP_HUBS = 4u      /* do not process rows at/above the split threshold */
+};
+
+enum pna_query_what {
+  PNA_QUERY_ABI_VERSION = 0,
+  PNA_QUERY_SM_ARCH = 1,          /* 100 : compiled for sm_100a only */
+  PNA_QUERY_DEFAULT_SPLIT = 2,    /* default in-degree at which a row is split across warps */
+  PNA_QUERY_DEFAULT_CHUNK = 3,    /* default edges per chunk of a split row */
+  PNA_QUERY_DEVICE_SM_COUNT = 4,  /* multiProcessorCount of the current device (needs a GPU) */
+  PNA_QUERY_MAX_FEATURES = 5,     /* largest n_feat accepted by pna_aggregate_fwd */
+  PNA_QUERY_SIZEOF_CSR = 6,       /* sizeof(pna_csr_t): lets an FFI binding verify its struct layout */
+  PNA_QUERY_SIZEOF_AGG = 7        /* sizeof(pna_agg_t) */
+};
+
+/* ---- destination-sorted CSR ("sorts/segments edges by destination in CSR", north_star) ------------------
+ * Replaces what torch_scatter does implicitly on every call (scatter by edge_index[1], pna.py:153,157).
+ * Edges are ordered by destination, ties kept in original edge order (stable), duplicates and self loops kept:
+ *   rowptr[i]..rowptr[i+1]  = CSR slots of the in-edges of node i;  in-degree = difference
+ *   col[s]                  = source node of slot s
+ *   perm[s]                 = original edge id of slot s (to bring per-edge tensors into CSR order)
+ * Rows with in-degree >= split_threshold ("hubs") are additionally listed with a chunking of their slots so the
+ * aggregation can spread them over many warps:
+ *   hub_info[4*h+0..3]      = row, first chunk id, number of chunks, in-degree
+ *   chunk_items[2*c+0..1]   = hub index h, chunk index within the hub
+ */
+typedef struct pna_csr {
+  int64_t n_nodes;          /* in */
+  int64_t n_edges;          /* in */
+  int32_t split_threshold;  /* in: >= 2 */
+  int32_t chunk_edges;      /* in: 1..split_threshold */
+  int32_t* rowptr;          /* out [n_nodes+1] */
+  int32_t* col;             /* out [n_edges] */
+  int32_t* perm;            /* out [n_edges] */
+  int32_t* hub_info;        /* out [4*cap_hubs] */
+  int32_t* chunk_items;     /* out [2*cap_chunks] */
+  int64_t cap_hubs;         /* in: >= n_edges/split_threshold + 1 */
+  int64_t cap_chunks;       /* in: >= n_edges/chunk_edges + cap_hubs + 1 */
+  int64_t n_hubs;           /* out (host) */
+  int64_t n_chunks;         /* out (host) */
+  int32_t max_degree;       /* out (host) */
+  int32_t reserved;
+} pna_csr_t;
+
+/* Bytes of device scratch pna_csr_build needs for (n_nodes, n_edges) on the current device. */
+int pna_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, size_t* bytes);
+
+/* src[e] -> dst[e], e in [0, n_edges): int64 device arrays (edge_index[0], edge_index[1] of PyG;
+ * g.edges() of DGL).  Synchronises the stream once at the end to return the host-side counts and to report
+ * out-of-range endpoints (PNA_ERR_INDEX).  Call once per graph, not per layer. */
+int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* csr, void* workspace, size_t workspace_bytes,
+                  pna_stream_t stream);
+
+/* ---- the aggregation ("single hand-written sm_100a CUDA kernel", north_star) ------------------------------
+ * For every destination row i (PyG semantics; In(i) = slots rowptr[i]..rowptr[i+1], d = |In(i)|):
+ *   m_s   = gathered[col[s]] (+ row_bias[i] when given)          s in In(i)           pna.py:137-150 / :239-240
+ *   sum   = fp32 sum of m_s in slot order;  mean = sum / max(d,1)                      aggregators.py:9-14
+ *   min/max over m_s, 0 when d == 0                                                     aggregators.py:17-22
+ *   var   = (sum of m_s*m_s)/max(d,1) - mean*mean ; std = sqrt(max(var,0) + 1e-5)       aggregators.py:25-32
+ *   amplification = log(d+1)/avg_log ; attenuation = d ? avg_log/log(d+1) : 1           scalers.py:12-19
+ *   linear = d/avg_lin ; inverse_linear = d ? avg_lin/d : 1                             scalers.py:22-29
+ *   out[i, tower t, ((s*A + a)*Ft + f)] = scaler_s * aggr_a                            pna.py:154-159 (scaler-major)
+ * With n_towers = T the n_feat columns are T blocks of Ft = n_feat/T, and the output row is T blocks of
+ * (has_self + S*A)*Ft columns, i.e. the [N, T, (1+)S*A*Ft] tensor of pna.py:129-131 flattened; when self_feat is
+ * given, block t starts with self_feat[i, t*self_tower_stride : +Ft] (the torch.cat([x, out]) of pna.py:131).
+ * All accumulation, degree, log and scaling in fp32 for both dtypes; bf16 is converted on load / store.
+ */
+typedef struct pna_agg {
+  const void* gathered;      /* [n_src, n_feat] rows to gather (x for PNAConvSimple, V = x W_j^T + b for PNAConv) */
+  int64_t ld_gathered;       /* row pitch in elements */
+  const int32_t* rowptr;     /* [n_rows+1] */
+  const int32_t* col;        /* [n_edges]; NULL = identity (gathered[] holds per-edge messages already in CSR order) */
+  const void* row_bias;      /* nullable [n_rows, n_feat]: destination-side term added to every gathered row */
+  int64_t ld_row_bias;
+  const void* self_feat;     /* nullable: prepend self features to every tower block of the output row */
+  int64_t ld_self;
+  int64_t self_tower_stride; /* Ft when the input is divided between towers, 0 when it is repeated (pna.py:123-126) */
+  void* out;                 /* [n_rows, ld_out] */
+  int64_t ld_out;            /* >= n_towers * (has_self + S*A) * Ft */
+  int64_t n_rows;
+  int32_t n_feat;            /* total gathered width = n_towers * Ft */
+  int32_t n_towers;
+  int32_t dtype;             /* pna_dtype of gathered / row_bias / self_feat / out */
+  int32_t n_aggr;
+  uint32_t aggr_codes;
+  int32_t n_scalers;
+  uint32_t scaler_codes;
+  float avg_log;             /* avg_deg['log'] of the layer ctor (pna.py:84) */
+  float avg_lin;             /* avg_deg['lin'] (pna.py:83); only read by linear / inverse_linear */
+  uint32_t flags;            /* pna_flags */
+  int32_t split_threshold;   /* must equal the value the CSR was built with */
+  int32_t chunk_edges;
+  const int32_t* hub_info;   /* from pna_csr_t; may be NULL when n_hubs == 0 */
+  const int32_t* chunk_items;
+  int64_t n_hubs;
+  int64_t n_chunks;
+  float* hub_partials;       /* fp32 scratch [n_chunks * 4 * n_feat]; may be NULL when n_hubs == 0 */
+  const int32_t* row_ids;    /* nullable [n_row_ids]: process only these light rows (halo overlap); hubs unaffected */
+  int64_t n_row_ids;
+} pna_agg_t;
+
+int pna_aggregate_fwd(const pna_agg_t* desc, pna_stream_t stream);
+
+/* Backward of pna_aggregate_fwd w.r.t. the gathered rows (needed by every training loop,
+ * multitask_benchmark/util/train.py:148).  grad_out has the layout of out (self block, if any, is skipped);
+ * grad_gathered [n_src, n_feat] fp32 must be zero-initialised by the caller, contributions are accumulated with
+ * atomics; grad_row_bias (nullable) [n_rows, n_feat] fp32 is written.  min/max route to the first slot attaining
+ * the extremum (torch_scatter arg semantics). */
+int pna_aggregate_bwd(const pna_agg_t* desc, const void* grad_out, int64_t ld_grad_out, float* grad_gathered,
+                      int64_t ld_grad_gathered, float* grad_row_bias, int64_t ld_grad_row_bias, pna_stream_t stream);
+
+/* ---- halo rows for the destination-partitioned multi-GPU path (north_star: "single NCCL all-to-all for halo
+ * source features per layer"): dst[i, :] = src[idx[i], :], n_feat elements per row.  Used to pack the send buffer. */
+int pna_gather_rows(const void* src, int64_t ld_src, const int32_t* idx, int64_t n_idx, void* dst, int64_t ld_dst,
+                    int32_t n_feat, int32_t dtype, pna_stream_t stream);
+
+int pna_query(int what);
+const char* pna_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNA_B200_H */

@@ -1,0 +1,160 @@
+"""ctypes binding of ``libpna_sm100.so`` (the C ABI declared in ``include/pna_b200.h``).
+
+The shared library is the product; this module only loads it, mirrors its structs and turns its status
+codes into exceptions.  There is deliberately NO fallback: if the library is missing or a call fails the caller
+gets an exception, never a silent PyTorch/CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libpna_sm100.so")
+CUDA_SOURCES = [os.path.join(_HERE, "csrc", n) for n in
+                ("pna_aggregate.cu", "pna_aggregate_bwd.cu", "pna_csr.cu", "pna_misc.cu")]
+CUDA_HEADERS = [os.path.join(_HERE, "csrc", n) for n in ("common.cuh", "pna_aggregate.cuh")] + [
+    os.path.join(REPO_ROOT, "include", "pna_b200.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+# status codes / enums of include/pna_b200.h
+PNA_OK = 0
+PNA_F32, PNA_BF16 = 0, 1
+AGGR_CODES = {"sum": 0, "mean": 1, "min": 2, "max": 3, "var": 4, "std": 5}
+SCALER_CODES = {"identity": 0, "amplification": 1, "attenuation": 2, "linear": 3, "inverse_linear": 4}
+FLAG_ZERO_ISOLATED, FLAG_SKIP_LIGHT, FLAG_SKIP_HUBS = 1, 2, 4
+(QUERY_ABI_VERSION, QUERY_SM_ARCH, QUERY_DEFAULT_SPLIT, QUERY_DEFAULT_CHUNK, QUERY_DEVICE_SM_COUNT,
+ QUERY_MAX_FEATURES, QUERY_SIZEOF_CSR, QUERY_SIZEOF_AGG) = range(8)
+
+# every symbol the header declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = ("pna_csr_workspace_bytes", "pna_csr_build", "pna_aggregate_fwd", "pna_aggregate_bwd",
+                    "pna_gather_rows", "pna_query", "pna_last_error")
+
+
+class PnaError(RuntimeError):
+    """A libpna_sm100 call returned a negative status; the message is pna_last_error()."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libpna_sm100 status {status}: {message}")
+        self.status = status
+
+
+class CsrStruct(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int64), ("n_edges", C.c_int64),
+        ("split_threshold", C.c_int32), ("chunk_edges", C.c_int32),
+        ("rowptr", C.c_void_p), ("col", C.c_void_p), ("perm", C.c_void_p),
+        ("hub_info", C.c_void_p), ("chunk_items", C.c_void_p),
+        ("cap_hubs", C.c_int64), ("cap_chunks", C.c_int64),
+        ("n_hubs", C.c_int64), ("n_chunks", C.c_int64),
+        ("max_degree", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class AggStruct(C.Structure):
+    _fields_ = [
+        ("gathered", C.c_void_p), ("ld_gathered", C.c_int64),
+        ("rowptr", C.c_void_p), ("col", C.c_void_p),
+        ("row_bias", C.c_void_p), ("ld_row_bias", C.c_int64),
+        ("self_feat", C.c_void_p), ("ld_self", C.c_int64), ("self_tower_stride", C.c_int64),
+        ("out", C.c_void_p), ("ld_out", C.c_int64),
+        ("n_rows", C.c_int64),
+        ("n_feat", C.c_int32), ("n_towers", C.c_int32), ("dtype", C.c_int32),
+        ("n_aggr", C.c_int32), ("aggr_codes", C.c_uint32),
+        ("n_scalers", C.c_int32), ("scaler_codes", C.c_uint32),
+        ("avg_log", C.c_float), ("avg_lin", C.c_float),
+        ("flags", C.c_uint32),
+        ("split_threshold", C.c_int32), ("chunk_edges", C.c_int32),
+        ("hub_info", C.c_void_p), ("chunk_items", C.c_void_p),
+        ("n_hubs", C.c_int64), ("n_chunks", C.c_int64),
+        ("hub_partials", C.c_void_p),
+        ("row_ids", C.c_void_p), ("n_row_ids", C.c_int64),
+    ]
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile libpna_sm100.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = [s for s in CUDA_SOURCES if os.path.exists(s)]
+    deps = srcs + [h for h in CUDA_HEADERS if os.path.exists(h)]
+    if not force and os.path.exists(LIB_PATH):
+        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
+            return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """The loaded library.  Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  pna_b200 has no CPU or PyTorch fallback for its kernels.")
+        L = C.CDLL(LIB_PATH)
+        L.pna_last_error.restype = C.c_char_p
+        L.pna_last_error.argtypes = []
+        L.pna_query.restype = C.c_int
+        L.pna_query.argtypes = [C.c_int]
+        L.pna_csr_workspace_bytes.restype = C.c_int
+        L.pna_csr_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]
+        L.pna_csr_build.restype = C.c_int
+        L.pna_csr_build.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CsrStruct), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.pna_aggregate_fwd.restype = C.c_int
+        L.pna_aggregate_fwd.argtypes = [C.POINTER(AggStruct), C.c_void_p]
+        L.pna_aggregate_bwd.restype = C.c_int
+        L.pna_aggregate_bwd.argtypes = [C.POINTER(AggStruct), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                        C.c_int64, C.c_void_p]
+        L.pna_gather_rows.restype = C.c_int
+        L.pna_gather_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                      C.c_int32, C.c_void_p]
+        abi = L.pna_query(QUERY_ABI_VERSION)
+        if abi != 3:
+            raise ImportError(f"{LIB_PATH} has ABI version {abi}, this package needs 3: rebuild it")
+        if L.pna_query(QUERY_SIZEOF_CSR) != C.sizeof(CsrStruct) or L.pna_query(QUERY_SIZEOF_AGG) != C.sizeof(AggStruct):
+            raise ImportError("ctypes struct layout does not match include/pna_b200.h: rebuild libpna_sm100.so")
+        _lib = L
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != PNA_OK:
+        raise PnaError(status, lib().pna_last_error().decode("utf-8", "replace"))
+
+
+def query(what: int) -> int:
+    r = lib().pna_query(what)
+    if r < 0:
+        raise PnaError(r, lib().pna_last_error().decode("utf-8", "replace"))
+    return r
+
+
+def pack_codes(names, table, what) -> tuple[int, int]:
+    """Pack an ordered list of aggregator/scaler names into (count, 4-bit codes) as the header defines."""
+    if isinstance(names, str):
+        names = names.split()
+    names = list(names)
+    if not names:
+        raise ValueError(f"empty {what} list")
+    codes = 0
+    for i, n in enumerate(names):
+        if n not in table:
+            raise KeyError(f"unknown {what} {n!r}; known: {sorted(table)}")
+        codes |= table[n] << (4 * i)
+    return len(names), codes

@@ -1,0 +1,258 @@
+"""``pna_aggregate``: the PNA neighbourhood aggregation as one call into libpna_sm100.so.
+
+Replaces, for one layer call, the reference sequence (models/pytorch_geometric/pna.py:152-159 / :242-249):
+``index_select`` of x_j, six ``scatter_add`` + ``scatter_min`` + ``scatter_max`` + ``degree`` passes over an
+E x F message tensor (aggregators.py:9-32), three scaler passes (scalers.py:8-19) and three ``cat``s.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Mapping, Optional, Sequence, Union
+
+import torch
+
+from . import _lib
+from .csr import CSRGraph
+
+_DTYPES = {torch.float32: _lib.PNA_F32, torch.bfloat16: _lib.PNA_BF16}
+Names = Union[str, Sequence[str]]
+
+
+def _names(v: Names) -> list:
+    return v.split() if isinstance(v, str) else list(v)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _rows2d(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dim() != 2:
+        raise ValueError(f"{what} must be 2-D, got shape {tuple(t.shape)}")
+    if t.size(1) > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.size(0) > 1 and t.stride(0) < t.size(1):
+        t = t.contiguous()
+    return t
+
+
+def output_width(n_feat: int, n_aggr: int, n_scalers: int, has_self: bool) -> int:
+    return (n_aggr * n_scalers + (1 if has_self else 0)) * n_feat
+
+
+def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names, scalers: Names,
+                      avg_deg: Mapping[str, float], *, towers: int = 1, row_bias: Optional[torch.Tensor] = None,
+                      self_feat: Optional[torch.Tensor] = None, self_divided: bool = True,
+                      messages_in_csr_order: bool = False, zero_isolated: bool = False,
+                      out: Optional[torch.Tensor] = None, row_ids: Optional[torch.Tensor] = None,
+                      skip_light: bool = False, skip_hubs: bool = False) -> torch.Tensor:
+    """Run the CUDA aggregation (no autograd).  Returns ``[N, towers * (has_self + S*A) * Ft]``.
+
+    gathered : [n_src, F] rows that are gathered through ``csr.col`` (x for PNAConvSimple; V = x W_j^T + b for
+               PNAConv), or -- with ``messages_in_csr_order`` -- [E, F] per-edge messages already in CSR slot order.
+    row_bias : optional [N, F] destination-side term added to every gathered row of that destination.
+    self_feat: optional node features copied to the front of every tower block of the output row
+               (the ``torch.cat([x, out])`` of pna.py:131); ``self_divided`` tells whether tower t reads columns
+               ``t*Ft:(t+1)*Ft`` (divide_input=True) or the same ``0:Ft`` (repeat, pna.py:126).
+    """
+    if not gathered.is_cuda:
+        raise ValueError("pna_b200 kernels run on CUDA tensors only; there is no CPU fallback")
+    if gathered.dtype not in _DTYPES:
+        raise TypeError(f"unsupported dtype {gathered.dtype}; libpna_sm100 takes float32 and bfloat16")
+    dev = gathered.device
+    if csr.device != dev:
+        raise ValueError(f"CSR lives on {csr.device}, features on {dev}")
+    gathered = _rows2d(gathered, "gathered")
+    F = int(gathered.size(1))
+    N = csr.n_nodes
+    if F % towers != 0:
+        raise ValueError(f"feature width {F} not divisible by towers={towers}")
+    Ft = F // towers
+    if messages_in_csr_order:
+        if gathered.size(0) != csr.n_edges:
+            raise ValueError("messages_in_csr_order needs one row per CSR slot")
+    n_aggr, aggr_codes = _lib.pack_codes(aggregators, _lib.AGGR_CODES, "aggregator")
+    n_scal, scal_codes = _lib.pack_codes(scalers, _lib.SCALER_CODES, "scaler")
+    if row_bias is not None:
+        row_bias = _rows2d(row_bias.to(gathered.dtype), "row_bias")
+        if tuple(row_bias.shape) != (N, F):
+            raise ValueError(f"row_bias must be [{N}, {F}]")
+    if self_feat is not None:
+        self_feat = _rows2d(self_feat.to(gathered.dtype), "self_feat")
+        need = F if self_divided else Ft
+        if self_feat.size(0) != N or self_feat.size(1) != need:
+            raise ValueError(f"self_feat must be [{N}, {need}]")
+    width = towers * output_width(Ft, n_aggr, n_scal, self_feat is not None)
+    if out is None:
+        out = torch.empty((N, width), dtype=gathered.dtype, device=dev)
+    else:
+        if out.dtype != gathered.dtype or out.device != dev or out.dim() != 2 or out.size(0) != N or out.size(1) < width \
+                or out.stride(1) != 1:
+            raise ValueError("bad `out` buffer")
+    if row_ids is not None:
+        if row_ids.dtype != torch.int32 or not row_ids.is_contiguous() or row_ids.device != dev:
+            raise ValueError("row_ids must be a contiguous int32 tensor on the same device")
+    flags = (_lib.FLAG_ZERO_ISOLATED if zero_isolated else 0) | (_lib.FLAG_SKIP_LIGHT if skip_light else 0) | \
+            (_lib.FLAG_SKIP_HUBS if skip_hubs else 0)
+    partials = None if skip_hubs else csr.hub_partials(F)
+    d = _lib.AggStruct(
+        gathered=_ptr(gathered), ld_gathered=gathered.stride(0) if gathered.size(0) > 1 else F,
+        rowptr=_ptr(csr.rowptr), col=None if messages_in_csr_order else (_ptr(csr.col) if csr.n_edges else None),
+        row_bias=_ptr(row_bias), ld_row_bias=0 if row_bias is None else (row_bias.stride(0) if N > 1 else F),
+        self_feat=_ptr(self_feat), ld_self=0 if self_feat is None else (self_feat.stride(0) if N > 1 else self_feat.size(1)),
+        self_tower_stride=Ft if (self_feat is not None and self_divided) else 0,
+        out=_ptr(out), ld_out=out.stride(0) if N > 1 else out.size(1),
+        n_rows=N, n_feat=F, n_towers=towers, dtype=_DTYPES[gathered.dtype],
+        n_aggr=n_aggr, aggr_codes=aggr_codes, n_scalers=n_scal, scaler_codes=scal_codes,
+        avg_log=float(avg_deg["log"]), avg_lin=float(avg_deg.get("lin", 1.0)),
+        flags=flags, split_threshold=csr.split_threshold, chunk_edges=csr.chunk_edges,
+        hub_info=_ptr(csr.hub_info) if csr.n_hubs else None, chunk_items=_ptr(csr.chunk_items) if csr.n_hubs else None,
+        n_hubs=csr.n_hubs, n_chunks=csr.n_chunks, hub_partials=_ptr(partials),
+        row_ids=_ptr(row_ids), n_row_ids=0 if row_ids is None else int(row_ids.numel()))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pna_aggregate_fwd(C.byref(d), torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
+# ---- autograd ----------------------------------------------------------------------------------------------------
+def _scaler_values(deg: torch.Tensor, scalers: list, avg_deg: Mapping[str, float]) -> torch.Tensor:
+    """[N, S] fp32 scaler values (scalers.py:8-29)."""
+    degf = deg.to(torch.float32)
+    lg = torch.log(degf + 1)
+    cols = []
+    for s in scalers:
+        if s == "identity":
+            cols.append(torch.ones_like(degf))
+        elif s == "amplification":
+            cols.append(lg / avg_deg["log"])
+        elif s == "attenuation":
+            cols.append(torch.where(degf == 0, torch.ones_like(degf), avg_deg["log"] / lg))
+        elif s == "linear":
+            cols.append(degf / avg_deg["lin"])
+        elif s == "inverse_linear":
+            cols.append(torch.where(degf == 0, torch.ones_like(degf), avg_deg["lin"] / degf))
+        else:
+            raise KeyError(s)
+    return torch.stack(cols, 1)
+
+
+def _backward_torch(gathered, csr: CSRGraph, row_bias, messages_in_csr_order, aggregators, scalers, avg_deg, towers,
+                    has_self, grad_out, need_bias_grad):
+    """Gradient of the aggregation w.r.t. the gathered rows / row_bias with device-side torch ops.
+
+    d mean = g/cnt; d sum = g; d var = g*2(m-mean)/cnt; d std = g*[var>0](m-mean)/(cnt*std) (autograd of
+    aggregators.py:25-32); min/max route to the first slot attaining the extremum (torch_scatter arg semantics).
+    """
+    N, E = csr.n_nodes, csr.n_edges
+    F = gathered.size(1)
+    Ft = F // towers
+    A, S = len(aggregators), len(scalers)
+    dst = csr.dst_of_slot
+    col = None if messages_in_csr_order else csr.col.long()
+    go = grad_out.to(torch.float32).reshape(N, towers, (1 if has_self else 0) + S * A, Ft)
+    grad_self = go[:, :, 0, :] if has_self else None
+    go = go[:, :, (1 if has_self else 0):, :].reshape(N, towers, S, A, Ft)
+    scale = _scaler_values(csr.in_degree, scalers, avg_deg)                       # [N, S]
+    gA = (go * scale[:, None, :, None, None]).sum(2)                              # [N, T, A, Ft]
+    gA = gA.permute(0, 2, 1, 3).reshape(N, A, F)
+    m = gathered.to(torch.float32)
+    m = m if col is None else m.index_select(0, col)
+    if row_bias is not None:
+        m = m + row_bias.to(torch.float32).index_select(0, dst)
+    cnt = csr.in_degree.clamp(min=1).to(torch.float32).unsqueeze(1)
+    ssum = torch.zeros((N, F), dtype=torch.float32, device=m.device).index_add_(0, dst, m)
+    mean = ssum / cnt
+    grad_m = torch.zeros_like(m)
+    need_var = any(a in ("var", "std") for a in aggregators)
+    if need_var:
+        msq = torch.zeros((N, F), dtype=torch.float32, device=m.device).index_add_(0, dst, m * m) / cnt
+        var = msq - mean * mean
+        centred = m - mean.index_select(0, dst)
+    slot = torch.arange(E, device=m.device).unsqueeze(1)
+    for a, name in enumerate(aggregators):
+        g = gA[:, a]
+        if name == "sum":
+            grad_m += g.index_select(0, dst)
+        elif name == "mean":
+            grad_m += (g / cnt).index_select(0, dst)
+        elif name == "var":
+            grad_m += (2.0 * g / cnt).index_select(0, dst) * centred
+        elif name == "std":
+            sd = torch.sqrt(torch.relu(var) + 1e-5)
+            coef = g * (var > 0).to(torch.float32) / (sd * cnt)
+            grad_m += coef.index_select(0, dst) * centred
+        elif name in ("min", "max"):
+            red = "amin" if name == "min" else "amax"
+            ext = torch.zeros((N, F), dtype=torch.float32, device=m.device).scatter_reduce_(
+                0, dst.unsqueeze(1).expand(E, F), m, red, include_self=False)
+            hit = m == ext.index_select(0, dst)
+            cand = torch.where(hit, slot.expand(E, F), torch.full((1, 1), E, device=m.device, dtype=slot.dtype))
+            first = torch.full((N, F), E, dtype=cand.dtype, device=m.device).scatter_reduce_(
+                0, dst.unsqueeze(1).expand(E, F), cand, "amin", include_self=True)
+            grad_m += g.index_select(0, dst) * (cand == first.index_select(0, dst)).to(torch.float32)
+        else:
+            raise KeyError(name)
+    if col is None:
+        grad_g = grad_m
+    else:
+        grad_g = torch.zeros((gathered.size(0), F), dtype=torch.float32, device=m.device).index_add_(0, col, grad_m)
+    grad_b = None
+    if need_bias_grad:
+        grad_b = torch.zeros((N, F), dtype=torch.float32, device=m.device).index_add_(0, dst, grad_m)
+    return grad_g, grad_b, grad_self
+
+
+class _PNAAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gathered, row_bias, self_feat, csr, aggregators, scalers, avg_deg, towers, self_divided,
+                messages_in_csr_order, zero_isolated):
+        out = aggregate_forward(gathered, csr, aggregators, scalers, avg_deg, towers=towers, row_bias=row_bias,
+                                self_feat=self_feat, self_divided=self_divided,
+                                messages_in_csr_order=messages_in_csr_order, zero_isolated=zero_isolated)
+        ctx.save_for_backward(gathered, row_bias, self_feat)
+        ctx.meta = (csr, _names(aggregators), _names(scalers), dict(avg_deg), towers, self_divided, messages_in_csr_order)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gathered, row_bias, self_feat = ctx.saved_tensors
+        csr, aggregators, scalers, avg_deg, towers, self_divided, in_order = ctx.meta
+        grad_g, grad_b, grad_self = _backward_torch(
+            gathered, csr, row_bias, in_order, aggregators, scalers, avg_deg, towers, self_feat is not None,
+            grad_out, ctx.needs_input_grad[1])
+        gs = None
+        if self_feat is not None and ctx.needs_input_grad[2]:
+            # [N, T, Ft] -> divided: [N, F]; repeated: sum over towers
+            gs = grad_self.reshape(csr.n_nodes, -1) if self_divided else grad_self.sum(1)
+            gs = gs.to(self_feat.dtype)
+        return (grad_g.to(gathered.dtype) if ctx.needs_input_grad[0] else None,
+                grad_b.to(row_bias.dtype) if (grad_b is not None) else None, gs,
+                None, None, None, None, None, None, None, None)
+
+
+def pna_aggregate(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names, scalers: Names,
+                  avg_deg: Mapping[str, float], *, towers: int = 1, row_bias: Optional[torch.Tensor] = None,
+                  self_feat: Optional[torch.Tensor] = None, self_divided: bool = True,
+                  messages_in_csr_order: bool = False, zero_isolated: bool = False) -> torch.Tensor:
+    """Differentiable PNA aggregation (forward = one libpna_sm100 call).  See :func:`aggregate_forward`."""
+    needs_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (gathered, row_bias, self_feat))
+    if not needs_grad:
+        return aggregate_forward(gathered, csr, aggregators, scalers, avg_deg, towers=towers, row_bias=row_bias,
+                                 self_feat=self_feat, self_divided=self_divided,
+                                 messages_in_csr_order=messages_in_csr_order, zero_isolated=zero_isolated)
+    return _PNAAggregate.apply(gathered, row_bias, self_feat, csr, aggregators, scalers, avg_deg, towers, self_divided,
+                               messages_in_csr_order, zero_isolated)
+
+
+def avg_deg_from_histogram(deg: torch.Tensor) -> dict:
+    """The ``avg_deg`` dictionary of the PyG ctor, op for op (pna.py:79-86)."""
+    deg = deg.to(torch.float)
+    total_no_vertices = deg.sum()
+    bin_degrees = torch.arange(len(deg), device=deg.device)
+    return {
+        "lin": ((bin_degrees * deg).sum() / total_no_vertices).item(),
+        "log": (((bin_degrees + 1).log() * deg).sum() / total_no_vertices).item(),
+        "exp": ((bin_degrees.exp() * deg).sum() / total_no_vertices).item(),
+    }

@@ -1,0 +1,143 @@
+"""Destination-sorted CSR of a graph, built once per graph by ``pna_csr_build`` and reused by every layer.
+
+The reference re-derives the segmentation on every ``aggregate`` call (torch_scatter by ``edge_index[1]``,
+reference models/pytorch_geometric/pna.py:153,157).  Every layer of a net -- and every one of the N/2 repeated
+layers of the multitask model (models/pytorch/gnn_framework.py:90-94) -- sees the same graph, so the CSR is cached
+by graph identity.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class CSRGraph:
+    """In-edges of every node, segmented by destination (stable in edge order)."""
+    n_nodes: int
+    n_edges: int
+    rowptr: torch.Tensor          # int32 [N+1]
+    col: torch.Tensor             # int32 [E]  source node of each slot
+    perm: torch.Tensor            # int32 [E]  original edge id of each slot
+    split_threshold: int
+    chunk_edges: int
+    hub_info: torch.Tensor        # int32 [n_hubs, 4]  row, first chunk, n chunks, in-degree
+    chunk_items: torch.Tensor     # int32 [n_chunks, 2]
+    n_hubs: int
+    n_chunks: int
+    max_degree: int
+    _partials: dict = field(default_factory=dict, repr=False)
+    _deg: Optional[torch.Tensor] = field(default=None, repr=False)
+    _dst: Optional[torch.Tensor] = field(default=None, repr=False)
+
+    @property
+    def device(self) -> torch.device:
+        return self.rowptr.device
+
+    @property
+    def in_degree(self) -> torch.Tensor:
+        """int32 [N] in-degree, duplicates included (= torch_geometric.utils.degree(edge_index[1], N))."""
+        if self._deg is None:
+            self._deg = self.rowptr[1:] - self.rowptr[:-1]
+        return self._deg
+
+    @property
+    def dst_of_slot(self) -> torch.Tensor:
+        """int64 [E] destination row of each CSR slot."""
+        if self._dst is None:
+            self._dst = torch.repeat_interleave(
+                torch.arange(self.n_nodes, device=self.device), self.in_degree.long(), output_size=self.n_edges)
+        return self._dst
+
+    def hub_partials(self, n_feat: int) -> Optional[torch.Tensor]:
+        """fp32 scratch for the split rows, [n_chunks, 4, n_feat]; allocated once per width."""
+        if self.n_hubs == 0:
+            return None
+        buf = self._partials.get(n_feat)
+        if buf is None:
+            buf = torch.empty((self.n_chunks, 4, n_feat), dtype=torch.float32, device=self.device)
+            self._partials[n_feat] = buf
+        return buf
+
+    def degree_histogram(self) -> torch.Tensor:
+        """Histogram of in-degrees (the ``deg`` ctor argument of PNAConv; reference example.py:21-25)."""
+        return torch.bincount(self.in_degree.long(), minlength=self.max_degree + 1)
+
+
+def build_csr(src: torch.Tensor, dst: torch.Tensor, n_nodes: int, split_threshold: Optional[int] = None,
+              chunk_edges: Optional[int] = None) -> CSRGraph:
+    """Build the CSR on the GPU through the C ABI.  ``src[e] -> dst[e]``; int64 CUDA tensors."""
+    if not src.is_cuda or not dst.is_cuda:
+        raise ValueError("pna_b200.build_csr needs CUDA tensors (there is no CPU path)")
+    if src.dtype != torch.int64 or dst.dtype != torch.int64:
+        src, dst = src.long(), dst.long()
+    src = src.contiguous()
+    dst = dst.contiguous()
+    E = int(src.numel())
+    if int(dst.numel()) != E:
+        raise ValueError("src and dst differ in length")
+    N = int(n_nodes)
+    dev = src.device
+    split = int(split_threshold) if split_threshold is not None else _lib.query(_lib.QUERY_DEFAULT_SPLIT)
+    chunk = int(chunk_edges) if chunk_edges is not None else min(_lib.query(_lib.QUERY_DEFAULT_CHUNK), split)
+    cap_hubs = E // split + 1
+    cap_chunks = E // chunk + cap_hubs + 1
+    with torch.cuda.device(dev):
+        rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(E, dtype=torch.int32, device=dev)
+        perm = torch.empty(E, dtype=torch.int32, device=dev)
+        hub_info = torch.empty((cap_hubs, 4), dtype=torch.int32, device=dev)
+        chunk_items = torch.empty((cap_chunks, 2), dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        nbytes = C.c_size_t(0)
+        _lib.check(L.pna_csr_workspace_bytes(N, E, C.byref(nbytes)))
+        ws = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=dev)
+        st = _lib.CsrStruct(
+            n_nodes=N, n_edges=E, split_threshold=split, chunk_edges=chunk,
+            rowptr=rowptr.data_ptr(), col=col.data_ptr() if E else None, perm=perm.data_ptr() if E else None,
+            hub_info=hub_info.data_ptr(), chunk_items=chunk_items.data_ptr(), cap_hubs=cap_hubs, cap_chunks=cap_chunks)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.pna_csr_build(src.data_ptr() if E else None, dst.data_ptr() if E else None, C.byref(st),
+                                   ws.data_ptr(), ws.numel(), stream))
+    nh, nc = int(st.n_hubs), int(st.n_chunks)
+    return CSRGraph(n_nodes=N, n_edges=E, rowptr=rowptr, col=col, perm=perm, split_threshold=split, chunk_edges=chunk,
+                    hub_info=hub_info[:nh].clone() if nh else hub_info[:0], chunk_items=chunk_items[:nc].clone() if nc else chunk_items[:0],
+                    n_hubs=nh, n_chunks=nc, max_degree=int(st.max_degree))
+
+
+# ---- cache by graph identity ---------------------------------------------------------------------------------
+_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CACHE_SIZE = 16
+
+
+def csr_from_edge_index(edge_index: torch.Tensor, n_nodes: int, cache: bool = True) -> CSRGraph:
+    """CSR of a PyG ``edge_index`` (row 0 = source j, row 1 = target i; aggregation index = row 1).
+
+    Cached on (storage pointer, in-place version counter, shape, N, device): a new batch is a new tensor, an
+    in-place edit bumps ``_version``; the cache keeps a reference to the tensor so the pointer cannot be recycled.
+    """
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("edge_index must have shape [2, E]")
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), tuple(edge_index.stride()), int(n_nodes),
+           str(edge_index.device))
+    if cache:
+        hit = _CACHE.get(key)
+        if hit is not None:
+            _CACHE.move_to_end(key)
+            return hit[1]
+    g = build_csr(edge_index[0], edge_index[1], n_nodes)
+    if cache:
+        _CACHE[key] = (edge_index, g)
+        while len(_CACHE) > _CACHE_SIZE:
+            _CACHE.popitem(last=False)
+    return g
+
+
+def clear_csr_cache() -> None:
+    _CACHE.clear()

@@ -1,0 +1,183 @@
+// Device-side building blocks of the PNA aggregation (forward).
+//
+// Work decomposition (B200-first, not a translation of torch_scatter's atomics):
+//   * destination rows are independent; a row is owned by a group of G lanes (G = 1..32, a power of two),
+//     32/G rows per warp.  Lanes map to FEATURE columns: lane g owns the 16-byte chunks g, g+G, .. (K of them), so
+//     every gathered neighbour row is read as fully coalesced 128-bit loads and NO cross-lane reduction is needed;
+//   * the slots of a row are walked in CSR order, U at a time (U independent 128-bit loads in flight per lane),
+//     and accumulated sequentially in fp32 with unfused mul/add -- the same order and rounding as the reference's
+//     CPU scatter_add path, so rows below the split threshold reproduce it bit for bit up to log/div rounding;
+//   * rows at/above the split threshold ("hubs", power-law graphs) are cut into chunks of `chunk` slots; each chunk
+//     is reduced by its own lane group into fp32 partials, and a finalize pass merges a hub's partials in chunk
+//     order (deterministic, no atomics on the output) and runs the same epilogue;
+//   * the epilogue computes mean / var / std and the degree scalers in registers and writes the S*A row segments
+//     with streaming 128-bit stores, in the reference's scaler-major column order.
+#pragma once
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace pna {
+
+struct KParams {
+  const void* x; long long ldx;
+  const int* rowptr; const int* col;
+  const void* bias; long long ldb;
+  const void* self; long long lds; long long self_tstride;
+  void* out; long long ldo;
+  long long n_rows;
+  int F, T, Ft, Wt, has_self;
+  int nA, nS; unsigned acodes, scodes;
+  float avg_log, avg_lin;
+  unsigned flags;
+  int split, chunk;
+  const int* hub_info; const int* chunk_items; long long n_hubs, n_chunks;
+  float* partials;
+  const int* row_ids; long long n_row_ids;
+};
+
+template <int VEC>
+struct Acc {
+  float sum[VEC], sq[VEC], mn[VEC], mx[VEC];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { sum[v] = 0.f; sq[v] = 0.f; mn[v] = CUDART_INF_F; mx[v] = -CUDART_INF_F; }
+  }
+};
+
+// Which feature columns a lane owns and where they land in the output row.
+template <int VEC, int G, int K>
+struct FeatMap {
+  int f[K];     // first feature column of chunk k
+  int ooff[K];  // output column of (scaler 0, aggregator 0) for that chunk
+  int soff[K];  // output column of the self block for that chunk
+  int sin[K];   // column inside self_feat
+  bool ok[K];
+  __device__ __forceinline__ void init(const KParams& p, int gl, int fblock) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int ff = fblock + (gl + k * G) * VEC;
+      ok[k] = ff < p.F;
+      const int fc = ok[k] ? ff : 0;
+      const int t = fc / p.Ft;
+      const int ft = fc - t * p.Ft;
+      f[k] = fc;
+      soff[k] = t * p.Wt + ft;
+      ooff[k] = soff[k] + p.has_self * p.Ft;
+      sin[k] = (int)(t * p.self_tstride) + ft;
+    }
+  }
+};
+
+// Reduce slots [beg, end) of one row into acc, U slots per step.
+template <typename T, int VEC, int G, int K, int U>
+__device__ __forceinline__ void accumulate_slots(const KParams& p, const FeatMap<VEC, G, K>& fm, int beg, int end,
+                                                 const float (&bias)[K][VEC], bool has_bias, Acc<VEC> (&acc)[K]) {
+  const T* __restrict__ x = static_cast<const T*>(p.x);
+  const int* __restrict__ col = p.col;
+  for (int e = beg; e < end; e += U) {
+    int src[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = e + u;
+      src[u] = (s < end) ? (col ? __ldg(col + s) : s) : -1;
+    }
+    typename Io<T, VEC>::Raw raw[U][K];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (src[u] >= 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(x + (long long)src[u] * p.ldx + fm.f[k]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (src[u] >= 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (fm.ok[k]) {
+            float m[VEC];
+            Io<T, VEC>::unpack(raw[u][k], m);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              if (has_bias) m[i] = __fadd_rn(m[i], bias[k][i]);
+              acc[k].sum[i] = __fadd_rn(acc[k].sum[i], m[i]);
+              acc[k].sq[i] = __fadd_rn(acc[k].sq[i], __fmul_rn(m[i], m[i]));
+              acc[k].mn[i] = fminf(acc[k].mn[i], m[i]);
+              acc[k].mx[i] = fmaxf(acc[k].mx[i], m[i]);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// mean/var/std + scalers + the S*A streaming stores of one row.
+template <typename T, int VEC, int G, int K>
+__device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC, G, K>& fm, long long row, int deg,
+                                             const Acc<VEC> (&acc)[K]) {
+  const bool iso = deg == 0;
+  const float degf = (float)deg;
+  const float cnt = iso ? 1.0f : degf;                     // count.clamp_(1)
+  const float lg = logf(degf + 1.0f);
+  const float s_amp = __fdiv_rn(lg, p.avg_log);            // scalers.py:12-13
+  const float s_att = iso ? 1.0f : __fdiv_rn(p.avg_log, lg);   // scalers.py:16-19
+  const float s_lin = __fdiv_rn(degf, p.avg_lin);          // scalers.py:22-23
+  const float s_ilin = iso ? 1.0f : __fdiv_rn(p.avg_lin, degf);  // scalers.py:26-29
+  const bool zero_all = iso && (p.flags & PNA_FLAG_ZERO_ISOLATED);
+  T* __restrict__ orow = static_cast<T*>(p.out) + row * p.ldo;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    if (!fm.ok[k]) continue;
+    if (p.self) {
+      float sv[VEC];
+      Io<T, VEC>::load(static_cast<const T*>(p.self) + row * p.lds + fm.sin[k], sv);
+      Io<T, VEC>::store(orow + fm.soff[k], sv);
+    }
+    float mean[VEC], var[VEC], sd[VEC], mn[VEC], mx[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      mean[i] = __fdiv_rn(acc[k].sum[i], cnt);                                   // aggregators.py:13-14
+      const float msq = __fdiv_rn(acc[k].sq[i], cnt);
+      var[i] = __fsub_rn(msq, __fmul_rn(mean[i], mean[i]));                      // aggregators.py:25-28
+      sd[i] = __fsqrt_rn(__fadd_rn(fmaxf(var[i], 0.0f), 1e-5f));                 // aggregators.py:31-32
+      mn[i] = iso ? 0.0f : acc[k].mn[i];                                         // aggregators.py:17-22 (empty -> 0)
+      mx[i] = iso ? 0.0f : acc[k].mx[i];
+    }
+    for (int a = 0; a < p.nA; ++a) {
+      const unsigned ac = (p.acodes >> (4 * a)) & 15u;
+      float val[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float r;
+        switch (ac) {
+          case PNA_AGGR_SUM: r = acc[k].sum[i]; break;
+          case PNA_AGGR_MEAN: r = mean[i]; break;
+          case PNA_AGGR_MIN: r = mn[i]; break;
+          case PNA_AGGR_MAX: r = mx[i]; break;
+          case PNA_AGGR_VAR: r = var[i]; break;
+          default: r = sd[i]; break;
+        }
+        val[i] = r;
+      }
+      for (int s = 0; s < p.nS; ++s) {
+        const unsigned sc = (p.scodes >> (4 * s)) & 15u;
+        float scale;
+        switch (sc) {
+          case PNA_SCALE_IDENTITY: scale = 1.0f; break;
+          case PNA_SCALE_AMPLIFICATION: scale = s_amp; break;
+          case PNA_SCALE_ATTENUATION: scale = s_att; break;
+          case PNA_SCALE_LINEAR: scale = s_lin; break;
+          default: scale = s_ilin; break;
+        }
+        float o[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = zero_all ? 0.0f : __fmul_rn(val[i], scale);
+        Io<T, VEC>::store(orow + fm.ooff[k] + (s * p.nA + a) * p.Ft, o);
+      }
+    }
+  }
+}
+
+}  // namespace pna

@@ -1,0 +1,177 @@
+// pna_csr_build: edge list -> destination-sorted CSR + hub chunk plan.
+//
+// What torch_scatter does implicitly on every call (scatter by edge_index[1]; reference
+// models/pytorch_geometric/pna.py:153,157) is done here ONCE per graph: a stable LSD radix sort of
+// (dst, edge id) pairs over only ceil(log2 N) key bits, a binary-search row pointer, and a one-pass plan of the
+// rows that are long enough to be split across warps.  Stability keeps the slots of a row in original edge order,
+// which is the accumulation order of the reference's CPU scatter_add.
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace pna {
+
+struct Counters {  // device-side, copied back once at the end of the build
+  int n_hubs, n_chunks, max_degree, err;
+};
+
+__global__ void k_prepare_keys(const long long* __restrict__ src, const long long* __restrict__ dst, int E, long long N,
+                               int* __restrict__ keys, int* __restrict__ vals, Counters* ctr) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const long long d = dst[e], s = src[e];
+  const bool bad = d < 0 || d >= N || s < 0 || s >= N;
+  if (bad) atomicOr(&ctr->err, 1);
+  keys[e] = bad ? 0 : (int)d;
+  vals[e] = e;
+}
+
+__global__ void k_fill_col(const long long* __restrict__ src, const int* __restrict__ perm, int E, long long N,
+                           int* __restrict__ col) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E) return;
+  const long long s = src[perm[i]];
+  col[i] = (s < 0 || s >= N) ? 0 : (int)s;
+}
+
+// rowptr[r] = number of sorted keys < r  (lower bound), r in [0, N]
+__global__ void k_rowptr(const int* __restrict__ keys, int E, long long N, int* __restrict__ rowptr) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > N) return;
+  int lo = 0, hi = E;
+  while (lo < hi) {
+    const int mid = (int)(((long long)lo + hi) >> 1);
+    if ((long long)keys[mid] < r) lo = mid + 1; else hi = mid;
+  }
+  rowptr[r] = lo;
+}
+
+__global__ void k_plan_hubs(const int* __restrict__ rowptr, long long N, int split, int chunk, int* __restrict__ hub_info,
+                            int* __restrict__ chunk_items, long long cap_hubs, long long cap_chunks, Counters* ctr) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int deg = 0;
+  if (r < N) deg = rowptr[r + 1] - rowptr[r];
+  // one atomicMax per warp
+  int m = deg;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&ctr->max_degree, m);
+  if (r >= N || deg < split) return;
+  const int nch = (deg + chunk - 1) / chunk;
+  const int h = atomicAdd(&ctr->n_hubs, 1);
+  const int first = atomicAdd(&ctr->n_chunks, nch);
+  if (h >= cap_hubs || (long long)first + nch > cap_chunks) { atomicOr(&ctr->err, 2); return; }
+  hub_info[4 * h + 0] = (int)r;
+  hub_info[4 * h + 1] = first;
+  hub_info[4 * h + 2] = nch;
+  hub_info[4 * h + 3] = deg;
+  for (int j = 0; j < nch; ++j) {
+    chunk_items[2 * (first + j) + 0] = h;
+    chunk_items[2 * (first + j) + 1] = j;
+  }
+}
+
+static int key_bits(long long N) {
+  int b = 1;
+  while (b < 31 && (1ll << b) < N) ++b;
+  return b;
+}
+
+struct WsLayout {
+  size_t keys_in, keys_out, vals_in, counters, cub_temp, cub_bytes, total;
+};
+
+static int ws_layout(long long N, long long E, WsLayout* L) {
+  size_t cub_bytes = 0;
+  const int n = (int)(E > 0 ? E : 1);
+  PNA_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr,
+                                                (int*)nullptr, n, 0, key_bits(N)));
+  size_t off = 0;
+  const size_t eb = align_up((size_t)n * sizeof(int), 256);
+  L->keys_in = off; off += eb;
+  L->keys_out = off; off += eb;
+  L->vals_in = off; off += eb;
+  L->counters = off; off += 256;
+  L->cub_temp = off; off += align_up(cub_bytes, 256);
+  L->cub_bytes = cub_bytes;
+  L->total = off;
+  return PNA_OK;
+}
+
+}  // namespace pna
+
+using namespace pna;
+
+extern "C" int pna_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, size_t* bytes) {
+  PNA_REQUIRE(bytes != nullptr, PNA_ERR_BAD_ARG, "pna_csr_workspace_bytes: null out pointer");
+  PNA_REQUIRE(n_nodes >= 0 && n_edges >= 0, PNA_ERR_BAD_ARG, "pna_csr_workspace_bytes: negative size");
+  PNA_REQUIRE(n_nodes < 0x7fffffffll && n_edges < 0x7fffffffll, PNA_ERR_UNSUPPORTED,
+              "pna_csr_workspace_bytes: n_nodes/n_edges must be < 2^31 (int32 CSR)");
+  WsLayout L;
+  const int rc = ws_layout(n_nodes, n_edges, &L);
+  if (rc != PNA_OK) return rc;
+  *bytes = L.total;
+  return PNA_OK;
+}
+
+extern "C" int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* csr, void* workspace, size_t workspace_bytes,
+                             pna_stream_t stream) {
+  PNA_REQUIRE(csr != nullptr, PNA_ERR_BAD_ARG, "pna_csr_build: null csr");
+  const long long N = csr->n_nodes, E = csr->n_edges;
+  PNA_REQUIRE(N >= 0 && E >= 0, PNA_ERR_BAD_ARG, "pna_csr_build: negative size");
+  PNA_REQUIRE(N < 0x7fffffffll && E < 0x7fffffffll, PNA_ERR_UNSUPPORTED, "pna_csr_build: n_nodes/n_edges must be < 2^31");
+  PNA_REQUIRE(csr->split_threshold >= 2 && csr->chunk_edges >= 1 && csr->chunk_edges <= csr->split_threshold, PNA_ERR_BAD_ARG,
+              "pna_csr_build: need split_threshold >= 2 and 1 <= chunk_edges <= split_threshold");
+  PNA_REQUIRE(csr->rowptr != nullptr, PNA_ERR_BAD_ARG, "pna_csr_build: null rowptr");
+  PNA_REQUIRE(E == 0 || (src && dst && csr->col && csr->perm), PNA_ERR_BAD_ARG, "pna_csr_build: null src/dst/col/perm");
+  PNA_REQUIRE(csr->cap_hubs >= E / csr->split_threshold + 1, PNA_ERR_WORKSPACE, "pna_csr_build: cap_hubs too small");
+  PNA_REQUIRE(csr->cap_chunks >= E / csr->chunk_edges + csr->cap_hubs + 1, PNA_ERR_WORKSPACE, "pna_csr_build: cap_chunks too small");
+  PNA_REQUIRE(csr->hub_info && csr->chunk_items, PNA_ERR_BAD_ARG, "pna_csr_build: null hub_info/chunk_items");
+  WsLayout L;
+  int rc = ws_layout(N, E, &L);
+  if (rc != PNA_OK) return rc;
+  PNA_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, PNA_ERR_WORKSPACE,
+              "pna_csr_build: workspace %zu bytes < required %zu", workspace_bytes, L.total);
+  PNA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, PNA_ERR_BAD_ARG, "pna_csr_build: workspace must be 256-byte aligned");
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  int* keys_in = reinterpret_cast<int*>(ws + L.keys_in);
+  int* keys_out = reinterpret_cast<int*>(ws + L.keys_out);
+  int* vals_in = reinterpret_cast<int*>(ws + L.vals_in);
+  Counters* ctr = reinterpret_cast<Counters*>(ws + L.counters);
+  PNA_CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(Counters), st));
+
+  const int TB = 256;
+  if (E > 0) {
+    const int nE = (int)E;
+    const unsigned gE = (unsigned)((E + TB - 1) / TB);
+    k_prepare_keys<<<gE, TB, 0, st>>>(reinterpret_cast<const long long*>(src), reinterpret_cast<const long long*>(dst), nE, N,
+                                      keys_in, vals_in, ctr);
+    PNA_CUDA_TRY(cudaGetLastError());
+    size_t cub_bytes = L.cub_bytes;
+    PNA_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, cub_bytes, (const int*)keys_in, keys_out, (const int*)vals_in,
+                                                  csr->perm, nE, 0, key_bits(N), st));
+    k_fill_col<<<gE, TB, 0, st>>>(reinterpret_cast<const long long*>(src), csr->perm, nE, N, csr->col);
+    PNA_CUDA_TRY(cudaGetLastError());
+  }
+  {
+    const unsigned gN = (unsigned)((N + 1 + TB - 1) / TB);
+    k_rowptr<<<gN, TB, 0, st>>>(keys_out, (int)E, N, csr->rowptr);
+    PNA_CUDA_TRY(cudaGetLastError());
+    if (N > 0) {
+      const unsigned gP = (unsigned)((N + TB - 1) / TB);
+      k_plan_hubs<<<gP, TB, 0, st>>>(csr->rowptr, N, csr->split_threshold, csr->chunk_edges, csr->hub_info, csr->chunk_items,
+                                     csr->cap_hubs, csr->cap_chunks, ctr);
+      PNA_CUDA_TRY(cudaGetLastError());
+    }
+  }
+  Counters host;
+  PNA_CUDA_TRY(cudaMemcpyAsync(&host, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  PNA_CUDA_TRY(cudaStreamSynchronize(st));
+  PNA_REQUIRE(!(host.err & 1), PNA_ERR_INDEX, "pna_csr_build: edge endpoint outside [0, %lld)", N);
+  PNA_REQUIRE(!(host.err & 2), PNA_ERR_WORKSPACE, "pna_csr_build: hub/chunk capacity exceeded");
+  csr->n_hubs = host.n_hubs;
+  csr->n_chunks = host.n_chunks;
+  csr->max_degree = host.max_degree;
+  return PNA_OK;
+}

@@ -1,0 +1,191 @@
+"""PyG-signature PNA layers backed by the sm_100a aggregation kernel.
+
+Drop-in for reference ``models/pytorch_geometric/pna.py``: same constructor arguments, same
+``forward(x, edge_index, edge_attr=None)``, same parameter names (``pre_nns.{t}.{k}``, ``post_nns.{t}.{k}``,
+``lin``, ``edge_encoder``; ``post_nn.{k}`` for the simple layer) so reference ``state_dict``s load unchanged.
+torch_geometric is NOT needed: ``MessagePassing.propagate`` (gather + scatter) is what the kernel replaces.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+from torch import Tensor
+from torch.nn import Linear, Module, ModuleList, ReLU, Sequential
+
+from .aggregate import avg_deg_from_histogram, pna_aggregate
+from .csr import CSRGraph, csr_from_edge_index
+
+_AGGRS = ("sum", "mean", "min", "max", "var", "std")          # aggregators.py:35-42
+_SCALERS = ("identity", "amplification", "attenuation", "linear", "inverse_linear")  # scalers.py:32-38
+
+
+def _reset(nn: Module) -> None:
+    """torch_geometric.nn.inits.reset: call reset_parameters on every child that has one."""
+    for m in nn.modules():
+        if m is not nn and hasattr(m, "reset_parameters"):
+            m.reset_parameters()
+
+
+def _check_names(aggregators: List[str], scalers: List[str]) -> None:
+    for a in aggregators:
+        if a not in _AGGRS:
+            raise KeyError(a)
+    for s in scalers:
+        if s not in _SCALERS:
+            raise KeyError(s)
+
+
+def _resolve_csr(x: Tensor, edge_index: Tensor, csr: Optional[CSRGraph]) -> CSRGraph:
+    if csr is not None:
+        if csr.n_nodes != x.size(0):
+            raise ValueError("csr.n_nodes does not match x")
+        return csr
+    return csr_from_edge_index(edge_index, x.size(0))
+
+
+class PNAConvSimple(Module):
+    """reference pna.py:167-254.  message = x_j, aggregate = 4 aggregators x 3 scalers, update = post_nn."""
+
+    def __init__(self, in_channels: int, out_channels: int, aggregators: List[str], scalers: List[str], deg: Tensor,
+                 post_layers: int = 1, **kwargs):
+        super().__init__()
+        _check_names(aggregators, scalers)
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.aggregators = list(aggregators)
+        self.scalers = list(scalers)
+        self.F_in = in_channels
+        self.F_out = out_channels
+        self.avg_deg: Dict[str, float] = avg_deg_from_histogram(deg)          # pna.py:212-219
+
+        width = len(aggregators) * len(scalers) * self.F_in                     # pna.py:221
+        modules = [Linear(width, self.F_out)]
+        for _ in range(post_layers - 1):
+            modules += [ReLU(), Linear(self.F_out, self.F_out)]
+        self.post_nn = Sequential(*modules)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        _reset(self.post_nn)
+
+    def aggregate_only(self, x: Tensor, edge_index: Optional[Tensor] = None, csr: Optional[CSRGraph] = None) -> Tensor:
+        """The [N, S*A*F] tensor ``propagate`` returns in the reference (pna.py:236)."""
+        csr = _resolve_csr(x, edge_index, csr)
+        return pna_aggregate(x, csr, self.aggregators, self.scalers, self.avg_deg)
+
+    def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Optional[Tensor] = None, *,
+                deg: Optional[Tensor] = None, csr: Optional[CSRGraph] = None) -> Tensor:
+        # `deg` (precomputed in-degree) is accepted for signature compatibility with BASELINE.json's wording; the
+        # in-degree always comes from the CSR row pointer, which is what degree(index) recounts in pna.py:247.
+        out = self.aggregate_only(x, edge_index, csr)
+        return self.post_nn(out)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels})"
+
+
+class PNAConv(Module):
+    """reference pna.py:17-164.  Towers, pre-MLP on [x_i || x_j (|| e)], aggregation, post-MLP on [x || agg], lin.
+
+    With ``pre_layers == 1`` and no edge features the message is affine in (x_i, x_j):
+    ``m = W_i x_i + W_j x_j + b`` (pna.py:94,147-149), so the E x F message tensor is never built: two node-level
+    GEMMs give ``U = x W_i^T`` and ``V = x W_j^T + b`` and the kernel gathers V and adds U[i] per slot.  Otherwise
+    the messages are materialised in CSR slot order and reduced by the same kernel.
+    """
+
+    def __init__(self, in_channels: int, out_channels: int, aggregators: List[str], scalers: List[str], deg: Tensor,
+                 edge_dim: Optional[int] = None, towers: int = 1, pre_layers: int = 1, post_layers: int = 1,
+                 divide_input: bool = False, **kwargs):
+        super().__init__()
+        if divide_input:
+            assert in_channels % towers == 0
+        assert out_channels % towers == 0
+        _check_names(aggregators, scalers)
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.aggregators = list(aggregators)
+        self.scalers = list(scalers)
+        self.edge_dim = edge_dim
+        self.towers = towers
+        self.divide_input = divide_input
+        self.pre_layers = pre_layers
+        self.F_in = in_channels // towers if divide_input else in_channels     # pna.py:76
+        self.F_out = out_channels // towers                                     # pna.py:77
+        self.avg_deg: Dict[str, float] = avg_deg_from_histogram(deg)            # pna.py:79-86
+
+        if self.edge_dim is not None:
+            self.edge_encoder = Linear(edge_dim, self.F_in)
+        self.pre_nns = ModuleList()
+        self.post_nns = ModuleList()
+        for _ in range(towers):
+            modules = [Linear((3 if edge_dim else 2) * self.F_in, self.F_in)]
+            for _ in range(pre_layers - 1):
+                modules += [ReLU(), Linear(self.F_in, self.F_in)]
+            self.pre_nns.append(Sequential(*modules))
+            width = (len(aggregators) * len(scalers) + 1) * self.F_in
+            modules = [Linear(width, self.F_out)]
+            for _ in range(post_layers - 1):
+                modules += [ReLU(), Linear(self.F_out, self.F_out)]
+            self.post_nns.append(Sequential(*modules))
+        self.lin = Linear(out_channels, out_channels)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        if self.edge_dim is not None:
+            self.edge_encoder.reset_parameters()
+        for nn in self.pre_nns:
+            _reset(nn)
+        for nn in self.post_nns:
+            _reset(nn)
+        self.lin.reset_parameters()
+
+    # -- message side ---------------------------------------------------------------------------------------------
+    def _affine_terms(self, x: Tensor):
+        """U = x W_i^T (destination side), V = x W_j^T + b (source side), both [N, T*F_in]."""
+        T, Fi = self.towers, self.F_in
+        Wi = [nn[0].weight[:, :Fi] for nn in self.pre_nns]
+        Wj = [nn[0].weight[:, Fi:2 * Fi] for nn in self.pre_nns]
+        b = torch.cat([nn[0].bias for nn in self.pre_nns])
+        if self.divide_input and T > 1:
+            # tower t only sees its own F_in input columns: block-diagonal [T*F_in, T*F_in] weight, one GEMM
+            U = x @ torch.block_diag(*Wi).t()
+            V = torch.addmm(b, x, torch.block_diag(*Wj).t())
+        else:
+            U = x @ torch.cat(Wi, 0).t()
+            V = torch.addmm(b, x, torch.cat(Wj, 0).t())
+        return U, V
+
+    def _messages_in_slot_order(self, x: Tensor, csr: CSRGraph, edge_attr: Optional[Tensor]) -> Tensor:
+        """General path (edge features or pre_layers > 1): pna.py:137-150 evaluated on CSR-ordered edges."""
+        T, Fi = self.towers, self.F_in
+        dst, src = csr.dst_of_slot, csr.col.long()
+        xt = x.view(-1, T, Fi) if self.divide_input else x.view(-1, 1, Fi).expand(-1, T, -1)
+        x_i, x_j = xt.index_select(0, dst), xt.index_select(0, src)
+        if edge_attr is not None:
+            e = self.edge_encoder(edge_attr).index_select(0, csr.perm.long())
+            h = torch.cat([x_i, x_j, e.view(-1, 1, Fi).expand(-1, T, -1)], dim=-1)
+        else:
+            h = torch.cat([x_i, x_j], dim=-1)
+        hs = [nn(h[:, t]) for t, nn in enumerate(self.pre_nns)]
+        return torch.cat(hs, dim=1)
+
+    def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Optional[Tensor] = None, *,
+                deg: Optional[Tensor] = None, csr: Optional[CSRGraph] = None) -> Tensor:
+        csr = _resolve_csr(x, edge_index, csr)
+        T = self.towers
+        common = dict(towers=T, self_feat=x, self_divided=self.divide_input)
+        if edge_attr is None and self.pre_layers == 1 and self.edge_dim is None:
+            U, V = self._affine_terms(x)
+            out = pna_aggregate(V, csr, self.aggregators, self.scalers, self.avg_deg, row_bias=U, **common)
+        else:
+            msgs = self._messages_in_slot_order(x, csr, edge_attr)
+            out = pna_aggregate(msgs, csr, self.aggregators, self.scalers, self.avg_deg, messages_in_csr_order=True,
+                                **common)
+        out = out.view(x.size(0), T, -1)                       # [N, T, (1 + S*A) * F_in]  (pna.py:131)
+        outs = [nn(out[:, t]) for t, nn in enumerate(self.post_nns)]
+        out = torch.cat(outs, dim=1) if T > 1 else outs[0]
+        return self.lin(out)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, towers={self.towers})"

@@ -1,0 +1,82 @@
+"""CPU-side checks of the C-ABI boundary: the library builds, loads and exports every symbol the header declares.
+No compute call is made here (no GPU in the authoring container)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import pna_b200
+from pna_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pna_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"^\s*(?:int|const char\*)\s+(pna_\w+)\s*\(", src, flags=re.M)))
+
+
+def test_library_is_built_and_loads():
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build()"
+    L = _lib.lib()
+    assert L.pna_query(_lib.QUERY_ABI_VERSION) == 3
+    assert L.pna_query(_lib.QUERY_SM_ARCH) == 100
+
+
+def test_every_declared_symbol_is_exported():
+    names = declared_functions()
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS)
+    L = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert getattr(L, n) is not None
+
+
+def test_struct_layouts_match_the_header():
+    assert _lib.query(_lib.QUERY_SIZEOF_CSR) == C.sizeof(_lib.CsrStruct)
+    assert _lib.query(_lib.QUERY_SIZEOF_AGG) == C.sizeof(_lib.AggStruct)
+
+
+def test_library_targets_sm_100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_queries_and_defaults_without_gpu():
+    assert _lib.query(_lib.QUERY_DEFAULT_SPLIT) >= 2
+    assert 1 <= _lib.query(_lib.QUERY_DEFAULT_CHUNK) <= _lib.query(_lib.QUERY_DEFAULT_SPLIT)
+    assert _lib.query(_lib.QUERY_MAX_FEATURES) >= 1024
+    with pytest.raises(pna_b200.PnaError) as ex:
+        _lib.query(12345)
+    assert ex.value.status == -1 and "selector" in str(ex.value)
+
+
+def test_bad_arguments_return_status_codes_not_aborts():
+    L = _lib.lib()
+    assert L.pna_aggregate_fwd(None, None) == -1
+    assert b"null descriptor" in L.pna_last_error()
+    d = _lib.AggStruct(n_rows=4, n_feat=8, n_towers=3, n_aggr=4, n_scalers=3)
+    assert L.pna_aggregate_fwd(C.byref(d), None) == -1            # 8 not divisible by 3 towers
+    d = _lib.AggStruct(n_rows=4, n_feat=8, n_towers=1, n_aggr=9, n_scalers=3)
+    assert L.pna_aggregate_fwd(C.byref(d), None) == -1
+    d = _lib.AggStruct(n_rows=4, n_feat=8, n_towers=1, n_aggr=1, aggr_codes=7, n_scalers=1)
+    assert L.pna_aggregate_fwd(C.byref(d), None) == -1            # aggregator code 7 does not exist
+    d = _lib.AggStruct(n_rows=4, n_feat=8, n_towers=1, n_aggr=1, n_scalers=1, dtype=5)
+    assert L.pna_aggregate_fwd(C.byref(d), None) == -2
+    d = _lib.AggStruct(n_rows=0, n_feat=8, n_towers=1, n_aggr=1, n_scalers=1)
+    assert L.pna_aggregate_fwd(C.byref(d), None) == 0             # empty problem: nothing to launch
+    nb = C.c_size_t(0)
+    assert L.pna_csr_workspace_bytes(-1, 0, C.byref(nb)) == -1
+    assert L.pna_csr_workspace_bytes(1 << 40, 0, C.byref(nb)) == -2
+    assert L.pna_gather_rows(None, 0, None, 0, None, 0, 8, 0, None) == 0
+    assert L.pna_gather_rows(None, 0, None, 5, None, 0, 8, 0, None) == -1
+
+
+def test_product_refuses_cpu_tensors():
+    with pytest.raises(ValueError):
+        pna_b200.build_csr(torch.zeros(2, dtype=torch.long), torch.zeros(2, dtype=torch.long), 2)

@@ -1,0 +1,347 @@
+"""Parity of the sm_100a path (through the C ABI) with the CPU oracle and the reference-generated golden vectors.
+
+Bar (BASELINE.json north_star): outputs within 1e-5 in fp32.  Used here as |got - want| <= 1e-5 + 1e-5*|want| on the
+aggregation output; layer outputs that go through a cuBLAS fp32 GEMM of width up to 13*F get 5e-5 (summation order of
+the GEMM differs between MKL and cuBLAS -- not a property of the aggregation).  bf16: 2^-8 relative + 1e-3 absolute
+against the fp32 oracle evaluated on the bf16-rounded inputs (SURVEY.md section 8a dtype notes).
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+A4 = ["mean", "max", "min", "std"]
+S3 = ["identity", "amplification", "attenuation"]
+TOL = dict(rtol=1e-5, atol=1e-5)
+LAYER_TOL = dict(rtol=5e-5, atol=5e-5)
+BF16_TOL = dict(rtol=2 ** -8, atol=1e-3)
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pna_b200
+    return pna_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import pna_oracle
+    return pna_oracle
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rand_graph(n, e, seed, hub=0, isolated=0.15):
+    g = torch.Generator().manual_seed(seed)
+    live = max(1, int(n * (1 - isolated)))
+    dst = torch.randint(0, live, (e,), generator=g)
+    src = torch.randint(0, n, (e,), generator=g)
+    if hub:
+        hs = torch.randint(0, n, (hub,), generator=g)
+        src = torch.cat([src, hs]); dst = torch.cat([dst, torch.full((hub,), n - 1)])
+        p = torch.randperm(src.numel(), generator=g)
+        src, dst = src[p], dst[p]
+    return torch.stack([src, dst])
+
+
+def avg_deg_of(ei, n, O):
+    return O.avg_deg_from_histogram(torch.bincount(torch.bincount(ei[1], minlength=n)))
+
+
+# ---- CSR ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,e,hub", [(1, 0, 0), (7, 0, 0), (1, 5, 0), (100, 1000, 0), (5000, 40000, 3000), (33, 2000, 0)])
+def test_csr_is_stable_sort_by_destination(P, n, e, hub):
+    ei = rand_graph(n, e, seed=n + e, hub=hub) if e else torch.zeros((2, 0), dtype=torch.long)
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+    order = torch.sort(ei[1], stable=True).indices
+    deg = torch.bincount(ei[1], minlength=n)
+    rowptr = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(deg, 0)])
+    assert torch.equal(csr.rowptr.cpu().long(), rowptr)
+    assert torch.equal(csr.perm.cpu().long(), order)
+    assert torch.equal(csr.col.cpu().long(), ei[0][order])
+    assert csr.max_degree == (int(deg.max()) if e else 0)
+    hubs = (deg >= csr.split_threshold).nonzero().flatten()
+    assert csr.n_hubs == hubs.numel()
+    info = csr.hub_info.cpu().long()
+    assert sorted(info[:, 0].tolist()) == hubs.tolist()
+    assert torch.equal(info[:, 3], deg[info[:, 0]])
+    assert torch.equal(info[:, 2], (deg[info[:, 0]] + csr.chunk_edges - 1) // csr.chunk_edges)
+    assert csr.n_chunks == int(info[:, 2].sum())
+    items = csr.chunk_items.cpu().long()
+    for h in range(csr.n_hubs):
+        first, nch = int(info[h, 1]), int(info[h, 2])
+        assert torch.equal(items[first:first + nch, 0], torch.full((nch,), h))
+        assert torch.equal(items[first:first + nch, 1], torch.arange(nch))
+
+
+def test_csr_rejects_out_of_range_endpoint(P):
+    ei = torch.tensor([[0, 1, 9], [1, 2, 0]])
+    with pytest.raises(P.PnaError) as ex:
+        P.build_csr(ei[0].to(dev()), ei[1].to(dev()), 3)
+    assert ex.value.status == -4
+
+
+# ---- aggregation vs oracle ---------------------------------------------------------------------------------------
+CASES = [
+    # n, e, F, hub
+    (300, 2500, 128, 0), (300, 2500, 64, 0), (300, 2500, 16, 0), (257, 1900, 4, 0), (64, 400, 1, 0), (64, 400, 3, 0),
+    (200, 1500, 75, 0), (200, 1500, 256, 0), (150, 900, 384, 0), (90, 700, 1024, 0), (120, 800, 130, 0),
+    (400, 3000, 128, 5000), (400, 3000, 32, 1500), (300, 1000, 75, 900), (128, 600, 512, 700),
+]
+
+
+@pytest.mark.parametrize("n,e,f,hub", CASES)
+def test_aggregate_matches_oracle_fp32(P, O, n, e, f, hub):
+    ei = rand_graph(n, e, seed=7 * n + f, hub=hub)
+    torch.manual_seed(n + f)
+    x = torch.randn(n, f)
+    avg = avg_deg_of(ei, n, O)
+    want = O.simple_propagate(x, ei, A4, S3, avg)
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+    got = P.aggregate_forward(x.to(dev()), csr, A4, S3, avg).cpu()
+    torch.testing.assert_close(got, want, **TOL)
+    # min / max columns are order independent: exact
+    fsl = slice(f, 3 * f)
+    assert torch.equal(got[:, fsl], want[:, fsl])
+    # rows below the split threshold follow the reference's accumulation order (edge order, unfused mul/add): the
+    # mean columns are bit-identical to torch's CPU scatter path; the std columns are bit-identical to the plain-C
+    # oracle (IEEE sqrtf) and within 1 ulp of torch, whose vectorised CPU sqrt is not correctly rounded
+    light = torch.bincount(ei[1], minlength=n) < csr.split_threshold
+    assert torch.equal(got[light][:, :f], want[light][:, :f])
+    torch.testing.assert_close(got[light][:, 3 * f:4 * f], want[light][:, 3 * f:4 * f], rtol=2.5e-7, atol=0)
+    from oracle import c_oracle
+    cwant = c_oracle.aggregate(x, ei, A4, ["identity"], avg)
+    assert torch.equal(got[light][:, :4 * f], cwant[light])
+
+
+def test_all_aggregators_and_scalers_any_order(P, O):
+    n, e, f = 220, 1800, 24
+    ei = rand_graph(n, e, seed=3, hub=600)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(1))
+    avg = avg_deg_of(ei, n, O)
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+    for aggrs, scalers in ((["sum", "mean", "min", "max", "var", "std"], ["identity", "amplification", "attenuation", "linear", "inverse_linear"]),
+                           (["std", "min"], ["attenuation"]), (["max"], ["inverse_linear", "identity"]),
+                           (["mean", "min", "max", "std"], S3)):
+        want = O.simple_propagate(x, ei, aggrs, scalers, avg)
+        got = P.aggregate_forward(x.to(dev()), csr, aggrs, scalers, avg).cpu()
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-5)   # 'sum' of a 600-edge hub: rtol carries it
+
+
+def test_isolated_rows_and_dgl_flavour(P, O):
+    n, f = 50, 8
+    ei = torch.tensor([[1, 2, 3], [0, 0, 4]])
+    x = torch.randn(n, f)
+    avg = {"log": 0.9, "lin": 1.1}
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+    got = P.aggregate_forward(x.to(dev()), csr, A4, S3, avg).cpu()
+    e5 = math.sqrt(1e-5)
+    iso = got[5]
+    assert torch.equal(iso[:3 * f], torch.zeros(3 * f))
+    torch.testing.assert_close(iso[3 * f:4 * f], torch.full((f,), e5), rtol=1e-7, atol=0)
+    assert torch.equal(iso[4 * f:8 * f], torch.zeros(4 * f))                 # amplification: log(1) = 0
+    assert torch.equal(iso[8 * f:], iso[:4 * f])                              # attenuation := 1 on isolated rows
+    torch.testing.assert_close(got, O.simple_propagate(x, ei, A4, S3, avg), **TOL)
+    dgl = P.aggregate_forward(x.to(dev()), csr, A4, S3, avg, zero_isolated=True).cpu()
+    want = O.dgl_reduce(x[ei[0]], None, ei[1], n, A4, S3, avg)
+    torch.testing.assert_close(dgl, want, **TOL)
+    assert dgl[5].abs().max() == 0
+
+
+def test_empty_graph_and_single_node(P, O):
+    for n in (1, 17):
+        ei = torch.zeros((2, 0), dtype=torch.long)
+        x = torch.randn(n, 12)
+        avg = {"log": 1.0, "lin": 1.0}
+        csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+        got = P.aggregate_forward(x.to(dev()), csr, A4, S3, avg).cpu()
+        torch.testing.assert_close(got, O.simple_propagate(x, ei, A4, S3, avg), **TOL)
+
+
+def test_degree_1e5_hub(P, O):
+    n, f = 2000, 16
+    ei = rand_graph(n, 6000, seed=11, hub=100_000)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(2))
+    avg = avg_deg_of(ei, n, O)
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+    assert csr.max_degree >= 100_000
+    got = P.aggregate_forward(x.to(dev()), csr, A4, S3, avg).cpu()
+    torch.testing.assert_close(got, O.simple_propagate(x, ei, A4, S3, avg), **TOL)
+
+
+def test_std_adversarial_identical_neighbours(P, O):
+    """ZINC-like: neighbourhoods of identical rows; the reference's E[m^2]-E[m]^2 leaves cancellation noise that the
+    sqrt(.+1e-5) amplifies ~158x.  Same accumulation order + unfused mul/add reproduces it exactly."""
+    from pna_b200 import synth
+    ei, x, _ = synth.zinc_like(n_graphs=400, n_feat=75, seed=3)
+    x = x * 3.0
+    n = x.size(0)
+    avg = avg_deg_of(ei, n, O)
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+    got = P.aggregate_forward(x.to(dev()), csr, A4, S3, avg).cpu()
+    want = O.simple_propagate(x, ei, A4, S3, avg)
+    torch.testing.assert_close(got, want, **TOL)
+    from oracle import c_oracle
+    assert torch.equal(got[:, :4 * 75], c_oracle.aggregate(x, ei, A4, ["identity"], avg))
+    # a "mathematically exact" variance (0 for identical neighbours) would NOT pass: the reference's noise is real
+    std_ref = want[:, 3 * 75:4 * 75]
+    assert float((std_ref - math.sqrt(1e-5)).abs().max()) > 1e-5
+
+
+def test_strided_and_misaligned_inputs_take_the_scalar_path(P, O):
+    n, e, f = 150, 1200, 32
+    ei = rand_graph(n, e, seed=5)
+    big = torch.randn(n, f + 3)
+    avg = avg_deg_of(ei, n, O)
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+    xs = big.to(dev())[:, 1:1 + f]            # row pitch f+3, base offset 4 bytes: not 16-byte aligned
+    got = P.aggregate_forward(xs, csr, A4, S3, avg).cpu()
+    torch.testing.assert_close(got, O.simple_propagate(big[:, 1:1 + f].contiguous(), ei, A4, S3, avg), **TOL)
+
+
+@pytest.mark.parametrize("n,e,f,hub", [(300, 2500, 128, 0), (200, 1500, 75, 0), (300, 2000, 64, 1000), (100, 700, 8, 0),
+                                       (100, 700, 272, 0)])
+def test_aggregate_bf16(P, O, n, e, f, hub):
+    ei = rand_graph(n, e, seed=n + f, hub=hub)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(f)).to(torch.bfloat16)
+    avg = avg_deg_of(ei, n, O)
+    want = O.simple_propagate(x.float(), ei, A4, S3, avg)
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+    got = P.aggregate_forward(x.to(dev()), csr, A4, S3, avg)
+    assert got.dtype == torch.bfloat16
+    torch.testing.assert_close(got.float().cpu(), want, **BF16_TOL)
+
+
+def test_row_subsets_and_skip_flags(P, O):
+    n, e, f = 500, 3000, 64
+    ei = rand_graph(n, e, seed=21, hub=800)
+    x = torch.randn(n, f)
+    avg = avg_deg_of(ei, n, O)
+    want = O.simple_propagate(x, ei, A4, S3, avg)
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+    out = torch.full((n, 12 * f), float("nan"), device=dev())
+    ids = torch.randperm(n)
+    a, b = ids[:200].sort().values.int().to(dev()), ids[200:].sort().values.int().to(dev())
+    P.aggregate_forward(x.to(dev()), csr, A4, S3, avg, out=out, row_ids=a, skip_hubs=True)
+    P.aggregate_forward(x.to(dev()), csr, A4, S3, avg, out=out, row_ids=b, skip_hubs=True)
+    P.aggregate_forward(x.to(dev()), csr, A4, S3, avg, out=out, skip_light=True)
+    torch.testing.assert_close(out.cpu(), want, **TOL)
+
+
+# ---- golden vectors produced by the reference's own files ------------------------------------------------------
+@pytest.mark.parametrize("name", ["pyg_simple_f16", "pyg_simple_f64_hub", "pyg_simple_f75_const", "pyg_simple_allops"])
+def test_golden_pnaconvsimple(P, name):
+    g = load_golden(name)
+    f = g["x"].size(1)
+    lay = P.PNAConvSimple(f, f, g["aggregators"], g["scalers"], g["deg"], post_layers=g["post_layers"])
+    lay.load_state_dict(g["state_dict"])          # reference parameter names load unchanged
+    lay = lay.to(dev())
+    assert lay.avg_deg["log"] == g["avg_deg"]["log"]
+    x, ei = g["x"].to(dev()), g["edge_index"].to(dev())
+    with torch.no_grad():
+        agg = lay.aggregate_only(x, ei).cpu()
+        out = lay(x, ei).cpu()
+    tol = dict(rtol=1e-5, atol=2e-5) if name == "pyg_simple_allops" else TOL
+    torch.testing.assert_close(agg, g["aggregate"], **tol)
+    torch.testing.assert_close(out, g["out"], **LAYER_TOL)
+
+
+@pytest.mark.parametrize("name", ["pyg_conv_t1", "pyg_conv_t4_div", "pyg_conv_t5_rep", "pyg_conv_edge", "pyg_conv_pre2",
+                                  "pyg_conv_multitask"])
+def test_golden_pnaconv(P, name):
+    g = load_golden(name)
+    c = g["ctor"]
+    lay = P.PNAConv(c["in_channels"], c["out_channels"], g["aggregators"], g["scalers"], g["deg"], edge_dim=c["edge_dim"],
+                    towers=c["towers"], pre_layers=c["pre_layers"], post_layers=c["post_layers"], divide_input=c["divide_input"])
+    lay.load_state_dict(g["state_dict"])
+    lay = lay.to(dev())
+    ea = None if g["edge_attr"] is None else g["edge_attr"].to(dev())
+    with torch.no_grad():
+        out = lay(g["x"].to(dev()), g["edge_index"].to(dev()), ea).cpu()
+    torch.testing.assert_close(out, g["out"], **LAYER_TOL)
+
+
+# ---- BASELINE.json config 2 at full size ---------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def arxiv(P):
+    from pna_b200 import synth
+    ei, x = synth.arxiv_like()
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), x.size(0))
+    return ei, x, csr
+
+
+def test_config2_full_size_vs_oracle(P, O, arxiv):
+    ei, x, csr = arxiv
+    n = x.size(0)
+    avg = avg_deg_of(ei, n, O)
+    want = O.simple_propagate(x, ei, A4, S3, avg)
+    got = P.aggregate_forward(x.to(dev()), csr, A4, S3, avg).cpu()
+    torch.testing.assert_close(got, want, **TOL)
+    assert csr.n_hubs > 0 and csr.max_degree > 5000          # the skewed destination distribution has hubs
+
+
+def test_config2_size_independent_properties(P, O, arxiv):
+    ei, x, csr = arxiv
+    n, f = x.shape
+    avg = avg_deg_of(ei, n, O)
+    xd = x.to(dev())
+    out = P.aggregate_forward(xd, csr, A4, S3, avg)
+    deg = csr.in_degree.float()
+    mean, mx, mn, sd = (out[:, i * f:(i + 1) * f] for i in range(4))
+    assert bool((mn <= mean + 1e-5).all()) and bool((mean <= mx + 1e-5).all())
+    assert bool((sd >= math.sqrt(1e-5) - 1e-9).all())
+    # scaler blocks are the identity block times a per-row constant
+    amp = (torch.log(deg + 1) / avg["log"]).unsqueeze(1)
+    att = torch.where(deg == 0, torch.ones_like(deg), avg["log"] / torch.log(deg + 1)).unsqueeze(1)
+    torch.testing.assert_close(out[:, 4 * f:8 * f], out[:, :4 * f] * amp, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(out[:, 8 * f:], out[:, :4 * f] * att, rtol=1e-6, atol=1e-7)
+    # sum of mean*deg over rows == column sums of the gathered sources (fp64 check of the gather itself)
+    tot = (mean.double() * deg.double().unsqueeze(1)).sum(0)
+    ref = xd.double().index_select(0, ei[0].to(dev())).sum(0)
+    torch.testing.assert_close(tot, ref, rtol=1e-5, atol=2e-2)
+    # a permutation of the edge list leaves min / max untouched and mean / std within rounding
+    p = torch.randperm(ei.size(1), generator=torch.Generator().manual_seed(1))
+    csr2 = P.build_csr(ei[0][p].to(dev()), ei[1][p].to(dev()), n)
+    out2 = P.aggregate_forward(xd, csr2, A4, S3, avg)
+    assert torch.equal(out2[:, f:3 * f], out[:, f:3 * f])
+    torch.testing.assert_close(out2, out, **TOL)
+    # x -> 2x: mean/min/max double exactly (power-of-two scaling commutes with fp32 rounding)
+    out3 = P.aggregate_forward(xd * 2, csr, A4, S3, avg)
+    assert torch.equal(out3[:, :3 * f], out[:, :3 * f] * 2)
+
+
+# ---- autograd through the drop-in layer --------------------------------------------------------------------------
+def test_backward_matches_reference_autograd(P, O):
+    n, e, f = 120, 900, 16
+    ei = rand_graph(n, e, seed=31, hub=400)
+    x = torch.randn(n, f)
+    deg = torch.bincount(torch.bincount(ei[1], minlength=n))
+    ref = O.PNAConvSimpleOracle(f, f, A4, S3, deg)
+    mine = P.PNAConvSimple(f, f, A4, S3, deg)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(dev())
+    xr = x.clone().requires_grad_(True)
+    xm = x.clone().to(dev()).requires_grad_(True)
+    w = torch.randn(n, f)
+    (ref(xr, ei) * w).sum().backward()
+    (mine(xm, ei.to(dev())) * w.to(dev())).sum().backward()
+    torch.testing.assert_close(xm.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(mine.post_nn[0].weight.grad.cpu(), ref.post_nn[0].weight.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_no_cpu_fallback(P):
+    csr_like = None
+    with pytest.raises(ValueError):
+        P.build_csr(torch.zeros(3, dtype=torch.long), torch.zeros(3, dtype=torch.long), 3)
+    ei = torch.zeros((2, 1), dtype=torch.long, device=dev())
+    csr = P.build_csr(ei[0], ei[1], 2)
+    with pytest.raises(ValueError):
+        P.aggregate_forward(torch.randn(2, 4), csr, A4, S3, {"log": 1.0})
+    with pytest.raises(TypeError):
+        P.aggregate_forward(torch.randn(2, 4, device=dev()).half(), csr, A4, S3, {"log": 1.0})

@@ -1,0 +1,82 @@
+"""Host-side logic of the drop-in layers that needs no GPU: names, packing, parameter compatibility, synthetic configs."""
+import pytest
+import torch
+
+import pna_b200
+from pna_b200 import _lib, synth
+from pna_b200.aggregate import output_width
+from conftest import load_golden
+
+
+def test_code_packing_follows_ctor_order():
+    n, codes = _lib.pack_codes(["mean", "max", "min", "std"], _lib.AGGR_CODES, "aggregator")
+    assert n == 4 and [(codes >> (4 * i)) & 15 for i in range(4)] == [1, 3, 2, 5]
+    n, codes = _lib.pack_codes("identity amplification attenuation", _lib.SCALER_CODES, "scaler")   # DGL string form
+    assert n == 3 and [(codes >> (4 * i)) & 15 for i in range(3)] == [0, 1, 2]
+    with pytest.raises(KeyError):
+        _lib.pack_codes(["moment3"], _lib.AGGR_CODES, "aggregator")
+    assert output_width(75, 4, 3, False) == 900 and output_width(15, 4, 3, True) == 195
+
+
+def test_avg_deg_matches_reference_ctor():
+    for name in ("pyg_simple_f16", "pyg_conv_t4_div"):
+        g = load_golden(name)
+        mine = pna_b200.avg_deg_from_histogram(g["deg"])
+        assert mine["log"] == g["avg_deg"]["log"] and mine["lin"] == g["avg_deg"]["lin"]
+
+
+@pytest.mark.parametrize("name", ["pyg_simple_f16", "pyg_simple_allops"])
+def test_reference_state_dict_loads_into_simple_layer(name):
+    g = load_golden(name)
+    f = g["x"].size(1)
+    lay = pna_b200.PNAConvSimple(f, f, g["aggregators"], g["scalers"], g["deg"], post_layers=g["post_layers"])
+    assert set(lay.state_dict()) == set(g["state_dict"])
+    lay.load_state_dict(g["state_dict"], strict=True)
+
+
+@pytest.mark.parametrize("name", ["pyg_conv_t1", "pyg_conv_t4_div", "pyg_conv_t5_rep", "pyg_conv_edge", "pyg_conv_pre2"])
+def test_reference_state_dict_loads_into_conv_layer(name):
+    g = load_golden(name)
+    c = g["ctor"]
+    lay = pna_b200.PNAConv(c["in_channels"], c["out_channels"], g["aggregators"], g["scalers"], g["deg"], edge_dim=c["edge_dim"],
+                           towers=c["towers"], pre_layers=c["pre_layers"], post_layers=c["post_layers"],
+                           divide_input=c["divide_input"])
+    assert set(lay.state_dict()) == set(g["state_dict"])
+    for k, v in lay.state_dict().items():
+        assert v.shape == g["state_dict"][k].shape, k
+    lay.load_state_dict(g["state_dict"], strict=True)
+
+
+def test_affine_message_decomposition_equals_per_edge_linear():
+    """m_e = pre_nn([x_i || x_j]) == U[i] + V[j] with U = x W_i^T, V = x W_j^T + b (pna.py:94,147-149)."""
+    g = load_golden("pyg_conv_t4_div")
+    c = g["ctor"]
+    lay = pna_b200.PNAConv(c["in_channels"], c["out_channels"], g["aggregators"], g["scalers"], g["deg"], towers=c["towers"],
+                           post_layers=c["post_layers"], divide_input=True)
+    lay.load_state_dict(g["state_dict"])
+    x, ei = g["x"], g["edge_index"]
+    with torch.no_grad():
+        U, V = lay._affine_terms(x)
+        xt = x.view(-1, lay.towers, lay.F_in)
+        h = torch.cat([xt[ei[1]], xt[ei[0]]], -1)
+        msg = torch.stack([nn(h[:, t]) for t, nn in enumerate(lay.pre_nns)], 1).reshape(ei.size(1), -1)
+    torch.testing.assert_close(U[ei[1]] + V[ei[0]], msg, rtol=1e-5, atol=1e-5)
+
+
+def test_synthetic_configs_have_the_stated_shapes():
+    ei, x = synth.arxiv_like(n_nodes=5000, n_edges=40000, n_feat=8)
+    assert ei.shape == (2, 40000) and x.shape == (5000, 8) and int(ei.max()) < 5000
+    deg = torch.bincount(ei[1], minlength=5000)
+    assert int(deg.max()) > 200 and int((deg == 0).sum()) > 50          # skewed: hubs and isolated rows
+    ei, x, batch = synth.zinc_like(n_graphs=50, n_feat=75)
+    assert x.size(1) == 75 and batch.numel() == x.size(0)
+    assert bool((batch[ei[0]] == batch[ei[1]]).all())                     # no edge crosses molecules
+    assert torch.equal(torch.sort(ei[0] * x.size(0) + ei[1]).values, torch.sort(ei[1] * x.size(0) + ei[0]).values)  # symmetric
+    ei, x = synth.superpixel_like(n_graphs=20, n_feat=4)
+    assert ei.size(1) == 20 * 70 * 8 and bool(((ei[0] // 70) == (ei[1] // 70)).all())
+    ei, x = synth.powerlaw(n_nodes=2000, n_edges=20000, n_feat=4)
+    assert int(torch.bincount(ei[1], minlength=2000).max()) > 500
+    ei, x = synth.multitask_like(n_graphs=3, nodes_per_graph=100)
+    assert x.shape == (300, 16)
+    b = synth.algorithmic_bytes(169343, 1166243, 128, 4, 1536)
+    assert abs(b["b_min"] / 1e9 - 1.13) < 0.01 and abs(b["b_gather"] / 1e9 - 1.64) < 0.01

@@ -1,0 +1,153 @@
+"""Pin oracle/pna_oracle.py against outputs of the reference's own files (tests/golden, made by oracle/gen_golden.py)."""
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import pna_oracle as O
+from conftest import load_golden
+
+SIMPLE = ["pyg_simple_f16", "pyg_simple_f64_hub", "pyg_simple_f75_const", "pyg_simple_allops"]
+CONV = ["pyg_conv_t1", "pyg_conv_t4_div", "pyg_conv_t5_rep", "pyg_conv_edge", "pyg_conv_pre2", "pyg_conv_multitask"]
+
+
+@pytest.mark.parametrize("name", SIMPLE)
+def test_simple_propagate_bit_exact(name):
+    g = load_golden(name)
+    agg = O.simple_propagate(g["x"], g["edge_index"], g["aggregators"], g["scalers"], g["avg_deg"])
+    assert torch.equal(agg, g["aggregate"])          # same torch ops in the same order -> bit identical
+    mine = O.avg_deg_from_histogram(g["deg"])
+    assert mine["lin"] == g["avg_deg"]["lin"] and mine["log"] == g["avg_deg"]["log"]   # 'exp' overflows to nan for hubs
+
+
+@pytest.mark.parametrize("name", SIMPLE)
+def test_simple_layer_forward(name):
+    g = load_golden(name)
+    f = g["x"].size(1)
+    lay = O.PNAConvSimpleOracle(f, f, g["aggregators"], g["scalers"], g["deg"], post_layers=g["post_layers"])
+    lay.load_state_dict(g["state_dict"])
+    with torch.no_grad():
+        out = lay(g["x"], g["edge_index"])
+    assert torch.equal(out, g["out"])
+
+
+@pytest.mark.parametrize("name", CONV)
+def test_conv_layer_forward(name):
+    g = load_golden(name)
+    c = g["ctor"]
+    lay = O.PNAConvOracle(c["in_channels"], c["out_channels"], g["aggregators"], g["scalers"], g["deg"], edge_dim=c["edge_dim"],
+                          towers=c["towers"], pre_layers=c["pre_layers"], post_layers=c["post_layers"],
+                          divide_input=c["divide_input"])
+    lay.load_state_dict(g["state_dict"])
+    x = g["x"]
+    xt = x.view(-1, c["towers"], lay.F_in) if c["divide_input"] else x.view(-1, 1, lay.F_in).repeat(1, c["towers"], 1)
+    with torch.no_grad():
+        agg = lay.propagate(xt, g["edge_index"], g["edge_attr"])
+        out = lay(x, g["edge_index"], g["edge_attr"])
+    assert torch.equal(agg, g["aggregate"])
+    assert torch.equal(out, g["out"])
+
+
+def test_dgl_reduce_matches_reference_mailbox_reduce():
+    g = load_golden("dgl_simple")
+    ei = g["edge_index"]
+    agg = O.dgl_reduce(g["h"][ei[0]], None, ei[1], g["h"].size(0), g["aggregators"].split(), g["scalers"].split(), g["avg_d"])
+    assert torch.equal(agg, g["aggregate"])
+    # in-degree-0 rows are all zero in the DGL flavour, std columns included
+    iso = torch.bincount(ei[1], minlength=g["h"].size(0)) == 0
+    assert iso.any() and agg[iso].abs().max() == 0
+
+
+def test_dgl_vs_pyg_flavours_differ_only_on_isolated_rows():
+    g = load_golden("dgl_simple")
+    ei, h = g["edge_index"], g["h"]
+    A, S = g["aggregators"].split(), g["scalers"].split()
+    d = O.dgl_reduce(h[ei[0]], None, ei[1], h.size(0), A, S, g["avg_d"])
+    p = O.simple_propagate(h, ei, A, S, g["avg_d"])
+    iso = torch.bincount(ei[1], minlength=h.size(0)) == 0
+    torch.testing.assert_close(d[~iso], p[~iso], rtol=2e-6, atol=2e-6)
+
+
+def test_k1_dense_reference_aggregators():
+    """the dense reference (imports unmodified) agrees with the scatter restatement."""
+    g = load_golden("dense_k1_k2")
+    adj, h = g["adj"][0], g["h"][0]
+    dst, src = adj.nonzero(as_tuple=True)            # adj[i, j] != 0  =>  edge j -> i
+    n = h.size(0)
+    msgs = h[src]
+    for name in ("mean", "std", "sum", "max", "min"):
+        mine = O.AGGREGATORS[name](msgs, dst, n)
+        torch.testing.assert_close(mine, g["k1"][name][0], rtol=1e-6, atol=1e-6)
+    agg = O.simple_propagate(h, torch.stack([src, dst]), ["mean", "max", "min", "std"],
+                             ["identity", "amplification", "attenuation"], g["avg_d"])
+    torch.testing.assert_close(agg, g["k1_scaled"][0], rtol=2e-6, atol=2e-6)
+
+
+def test_k2_numpy_label_reducers():
+    """float64 numpy neighbourhood reducers of the reference's dataset generator."""
+    g = load_golden("dense_k1_k2")
+    adj, h = g["adj"][0], g["h"][0]
+    dst, src = adj.nonzero(as_tuple=True)
+    n = h.size(0)
+    msgs = h[src]
+    torch.testing.assert_close(O.aggregate_mean(msgs, dst, n).double(), g["k2"]["mean"], rtol=1e-6, atol=1e-6)
+    assert torch.equal(O.aggregate_max(msgs, dst, n).double(), g["k2"]["max"])
+    assert torch.equal(O.aggregate_min(msgs, dst, n).double(), g["k2"]["min"])
+    std_no_eps = torch.sqrt(g["k2"]["std"] ** 2 + 1e-5)
+    torch.testing.assert_close(O.aggregate_std(msgs, dst, n).double(), std_no_eps, rtol=1e-5, atol=1e-6)
+
+
+def test_k3_analytic_rows():
+    """in-degree 0: [0, 0, 0, sqrt(1e-5)], amplification -> 0, attenuation -> unchanged; in-degree 1: var == 0."""
+    x = torch.tensor([[1.5, -2.0], [0.25, 4.0], [7.0, 7.0]])
+    ei = torch.tensor([[0], [1]])                    # single edge 0 -> 1; nodes 0 and 2 isolated
+    avg = {"log": 0.7, "lin": 1.3}
+    out = O.simple_propagate(x, ei, ["mean", "max", "min", "std"], ["identity", "amplification", "attenuation"], avg)
+    e = math.sqrt(1e-5)
+    row0 = torch.tensor([0, 0, 0, 0, 0, 0, e, e] + [0] * 8 + [0, 0, 0, 0, 0, 0, e, e], dtype=torch.float32)
+    torch.testing.assert_close(out[0], row0, rtol=0, atol=1e-9)
+    torch.testing.assert_close(out[2], row0, rtol=0, atol=1e-9)
+    amp, att = math.log(2.0) / 0.7, 0.7 / math.log(2.0)
+    base = torch.tensor([1.5, -2.0, 1.5, -2.0, 1.5, -2.0, e, e])
+    torch.testing.assert_close(out[1], torch.cat([base, base * amp, base * att]), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference checkout not on this machine")
+def test_live_reference_over_shims():
+    """In the authoring container, re-run the real reference file and compare with the oracle on fresh inputs."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import torch\n"
+        "from models.pytorch_geometric.pna import PNAConvSimple\n"
+        "from oracle import pna_oracle as O\n"
+        "torch.manual_seed(5); n,e,f=300,2000,24\n"
+        "x=torch.randn(n,f); ei=torch.randint(0,n,(2,e)); deg=torch.bincount(torch.bincount(ei[1],minlength=n))\n"
+        "A=['mean','min','max','std']; S=['identity','amplification','attenuation']\n"
+        "c=PNAConvSimple(f,f,A,S,deg); r=c.propagate(ei,x=x,size=None)\n"
+        "assert torch.equal(r,O.simple_propagate(x,ei,A,S,c.avg_deg)); print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "oracle", "shims"), "/root/reference", root]))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_c_oracle_agrees_with_torch_oracle():
+    """Two independent restatements: torch ops vs scalar C loops in edge order without FMA.  sum / mean / min / max /
+    var agree bit for bit (torch's CPU scatter_add_ IS sequential in edge order); sqrt and log differ by <= 1 ulp
+    (torch's vectorised CPU sqrt/log are not correctly rounded; glibc's are)."""
+    from oracle import c_oracle
+    g = torch.Generator().manual_seed(3)
+    n, e, f = 400, 5000, 19
+    ei = torch.randint(0, n - 40, (2, e), generator=g)
+    x = torch.randn(n, f, generator=g)
+    A = ["sum", "mean", "min", "max", "var", "std"]
+    S = ["identity", "amplification", "attenuation", "linear", "inverse_linear"]
+    avg = O.avg_deg_from_histogram(torch.bincount(torch.bincount(ei[1], minlength=n)))
+    t = O.simple_propagate(x, ei, A, S, avg)
+    c = c_oracle.aggregate(x, ei, A, S, avg)
+    assert torch.equal(t[:, :5 * f], c[:, :5 * f])
+    torch.testing.assert_close(t, c, rtol=3e-7, atol=1e-9)
+    d = O.dgl_reduce(x[ei[0]], None, ei[1], n, ["mean", "max", "min", "std"], S[:3], avg)
+    cd = c_oracle.aggregate(x, ei, ["mean", "max", "min", "std"], S[:3], avg, zero_isolated=True)
+    torch.testing.assert_close(d, cd, rtol=2e-6, atol=2e-6)
