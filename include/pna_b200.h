@@ -46,7 +46,10 @@ enum pna_dtype { PNA_F32 = 0, PNA_BF16 = 1 };
 
 /* Aggregator codes (order of appearance in the layer's ctor list fixes the column layout,
  * pna.py:70,153-154).  Packed 4 bits each, first aggregator in the low nibble. */
-enum pna_aggr { PNA_AGGR_SUM = 0, PNA_AGGR_MEAN = 1, PNA_AGGR_MIN = 2, PNA_AGGR_MAX = 3, PNA_AGGR_VAR = 4, PNA_AGGR_STD = 5 };
+enum pna_aggr { PNA_AGGR_SUM = 0, PNA_AGGR_MEAN = 1, PNA_AGGR_MIN = 2, PNA_AGGR_MAX = 3, PNA_AGGR_VAR = 4, PNA_AGGR_STD = 5,
+                PNA_AGGR_SKIP = 15 /* keep the column slot but do not write it: lets two calls with different edge
+                                       sets / messages fill one output row (dense reference layer, where max/min and
+                                       mean/std see different messages: models/pytorch/pna/aggregators.py:30-51) */ };
 /* Scaler codes (scalers.py:32-38), packed the same way. */
 enum pna_scaler { PNA_SCALE_IDENTITY = 0, PNA_SCALE_AMPLIFICATION = 1, PNA_SCALE_ATTENUATION = 2, PNA_SCALE_LINEAR = 3, PNA_SCALE_INVERSE_LINEAR = 4 };
 

@@ -8,7 +8,11 @@ from ._lib import PnaError, build_library
 from .aggregate import aggregate_forward, avg_deg_from_histogram, pna_aggregate
 from .csr import CSRGraph, build_csr, clear_csr_cache, csr_from_edge_index
 from .pyg import PNAConv, PNAConvSimple
+from .graph import Graph, avg_d_from_graphs, graph_csr
+from .dgl_layers import PNALayer, PNASimpleLayer
+from . import dense
 
 __all__ = ["PnaError", "build_library", "aggregate_forward", "avg_deg_from_histogram", "pna_aggregate", "CSRGraph",
-           "build_csr", "clear_csr_cache", "csr_from_edge_index", "PNAConv", "PNAConvSimple"]
+           "build_csr", "clear_csr_cache", "csr_from_edge_index", "PNAConv", "PNAConvSimple", "Graph", "avg_d_from_graphs",
+           "graph_csr", "PNALayer", "PNASimpleLayer", "dense"]
 __version__ = "0.1.0"

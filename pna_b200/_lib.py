@@ -15,17 +15,19 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libpna_sm100.so")
 CUDA_SOURCES = [os.path.join(_HERE, "csrc", n) for n in
-                ("pna_aggregate.cu", "pna_aggregate_bwd.cu", "pna_csr.cu", "pna_misc.cu")]
-CUDA_HEADERS = [os.path.join(_HERE, "csrc", n) for n in ("common.cuh", "pna_aggregate.cuh")] + [
+                ("pna_aggregate.cu", "pna_aggregate_f32_vec.cu", "pna_aggregate_f32_scalar.cu", "pna_aggregate_bf16_vec.cu",
+                 "pna_aggregate_bf16_scalar.cu", "pna_aggregate_bwd.cu", "pna_csr.cu", "pna_misc.cu")]
+CUDA_HEADERS = [os.path.join(_HERE, "csrc", n) for n in ("common.cuh", "pna_aggregate.cuh", "pna_aggregate_impl.cuh")] + [
     os.path.join(REPO_ROOT, "include", "pna_b200.h")]
+BUILD_DIR = os.path.join(_HERE, "csrc", "build")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+# sm_100a only: -gencode arch=compute_100a,code=sm_100a (no PTX for other targets, no multi-arch fat binary)
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 # status codes / enums of include/pna_b200.h
 PNA_OK = 0
 PNA_F32, PNA_BF16 = 0, 1
-AGGR_CODES = {"sum": 0, "mean": 1, "min": 2, "max": 3, "var": 4, "std": 5}
+AGGR_CODES = {"sum": 0, "mean": 1, "min": 2, "max": 3, "var": 4, "std": 5, "_skip": 15}
 SCALER_CODES = {"identity": 0, "amplification": 1, "attenuation": 2, "linear": 3, "inverse_linear": 4}
 FLAG_ZERO_ISOLATED, FLAG_SKIP_LIGHT, FLAG_SKIP_HUBS = 1, 2, 4
 (QUERY_ABI_VERSION, QUERY_SM_ARCH, QUERY_DEFAULT_SPLIT, QUERY_DEFAULT_CHUNK, QUERY_DEVICE_SM_COUNT,
@@ -77,17 +79,39 @@ class AggStruct(C.Structure):
     ]
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile libpna_sm100.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+def build_library(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
+    """Compile libpna_sm100.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    Every .cu is compiled to an object file in parallel (they are independent translation units), then linked with
+    ``nvcc -shared``.  Objects are rebuilt when their source or any header is newer.
+    """
+    from concurrent.futures import ThreadPoolExecutor
     srcs = [s for s in CUDA_SOURCES if os.path.exists(s)]
-    deps = srcs + [h for h in CUDA_HEADERS if os.path.exists(h)]
-    if not force and os.path.exists(LIB_PATH):
-        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
-            return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+    hdrs = [h for h in CUDA_HEADERS if os.path.exists(h)]
+    hdr_time = max(os.path.getmtime(h) for h in hdrs)
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    jobs, objs = [], []
+    for src in srcs:
+        obj = os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time)
+        if stale:
+            jobs.append(["nvcc"] + NVCC_FLAGS + list(extra_flags) + ["-c", src, "-o", obj])
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+        return r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        logs = list(ex.map(run, jobs))
+    if jobs or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs):
+        run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs)
+    if verbose and extra_flags:
+        print("\n".join(logs))
     return LIB_PATH
 
 

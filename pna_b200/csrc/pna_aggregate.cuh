@@ -35,6 +35,24 @@ struct KParams {
   const int* row_ids; long long n_row_ids;
 };
 
+// Compile-time aggregator / scaler lists for the configurations the reference's configs use; Dynamic reads them from
+// KParams.  A static list turns the epilogue into straight-line code (no uniform branches, no selects).
+struct CfgDynamic {
+  static constexpr bool kStatic = false;
+  static constexpr int NA = PNA_MAX_AGGR, NS = PNA_MAX_SCALERS;
+  static constexpr unsigned ACODES = 0, SCODES = 0;
+};
+template <int NA_, unsigned ACODES_, int NS_, unsigned SCODES_>
+struct CfgStatic {
+  static constexpr bool kStatic = true;
+  static constexpr int NA = NA_, NS = NS_;
+  static constexpr unsigned ACODES = ACODES_, SCODES = SCODES_;
+};
+// "mean max min std" x "identity amplification attenuation" (realworld_benchmark/configs/*.json) and the
+// "mean min max std" order of models/pytorch_geometric/example.py:33
+using CfgMeanMaxMinStd = CfgStatic<4, (1u) | (3u << 4) | (2u << 8) | (5u << 12), 3, (0u) | (1u << 4) | (2u << 8)>;
+using CfgMeanMinMaxStd = CfgStatic<4, (1u) | (2u << 4) | (3u << 8) | (5u << 12), 3, (0u) | (1u << 4) | (2u << 8)>;
+
 template <int VEC>
 struct Acc {
   float sum[VEC], sq[VEC], mn[VEC], mx[VEC];
@@ -53,6 +71,16 @@ struct FeatMap {
   int sin[K];   // column inside self_feat
   bool ok[K];
   __device__ __forceinline__ void init(const KParams& p, int gl, int fblock) {
+    if (p.T == 1 && !p.has_self) {   // one tower, no self block: the output column of a feature is the feature
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int ff = fblock + (gl + k * G) * VEC;
+        ok[k] = ff < p.F;
+        f[k] = ok[k] ? ff : 0;
+        ooff[k] = f[k]; soff[k] = 0; sin[k] = 0;
+      }
+      return;
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const int ff = fblock + (gl + k * G) * VEC;
@@ -68,44 +96,42 @@ struct FeatMap {
   }
 };
 
-// Reduce slots [beg, end) of one row into acc, U slots per step.
-template <typename T, int VEC, int G, int K, int U>
-__device__ __forceinline__ void accumulate_slots(const KParams& p, const FeatMap<VEC, G, K>& fm, int beg, int end,
+// One batch of U slots starting at e.  FULL: all U slots exist (no predicates in the instruction stream).
+template <typename T, int VEC, int G, int K, int U, bool FULL>
+__device__ __forceinline__ void accumulate_batch(const T* __restrict__ x, int ldx, const int* __restrict__ col,
+                                                 const FeatMap<VEC, G, K>& fm, int e, int end,
                                                  const float (&bias)[K][VEC], bool has_bias, Acc<VEC> (&acc)[K]) {
-  const T* __restrict__ x = static_cast<const T*>(p.x);
-  const int* __restrict__ col = p.col;
-  for (int e = beg; e < end; e += U) {
-    int src[U];
+  int src[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int s = e + u;
-      src[u] = (s < end) ? (col ? __ldg(col + s) : s) : -1;
+  for (int u = 0; u < U; ++u) {
+    const int s = e + u;
+    if (FULL) src[u] = col ? __ldg(col + s) : s;
+    else src[u] = (s < end) ? (col ? __ldg(col + s) : s) : -1;
+  }
+  typename Io<T, VEC>::Raw raw[U][K];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (FULL || src[u] >= 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(x + (long long)src[u] * ldx + fm.f[k]);
     }
-    typename Io<T, VEC>::Raw raw[U][K];
+  }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (src[u] >= 0) {
+  for (int u = 0; u < U; ++u) {
+    if (FULL || src[u] >= 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-          if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(x + (long long)src[u] * p.ldx + fm.f[k]);
-      }
-    }
+      for (int k = 0; k < K; ++k) {
+        if (fm.ok[k]) {
+          float m[VEC];
+          Io<T, VEC>::unpack(raw[u][k], m);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (src[u] >= 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if (fm.ok[k]) {
-            float m[VEC];
-            Io<T, VEC>::unpack(raw[u][k], m);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-              if (has_bias) m[i] = __fadd_rn(m[i], bias[k][i]);
-              acc[k].sum[i] = __fadd_rn(acc[k].sum[i], m[i]);
-              acc[k].sq[i] = __fadd_rn(acc[k].sq[i], __fmul_rn(m[i], m[i]));
-              acc[k].mn[i] = fminf(acc[k].mn[i], m[i]);
-              acc[k].mx[i] = fmaxf(acc[k].mx[i], m[i]);
-            }
+          for (int i = 0; i < VEC; ++i) {
+            if (has_bias) m[i] = __fadd_rn(m[i], bias[k][i]);
+            acc[k].sum[i] = __fadd_rn(acc[k].sum[i], m[i]);
+            acc[k].sq[i] = __fadd_rn(acc[k].sq[i], __fmul_rn(m[i], m[i]));
+            acc[k].mn[i] = fminf(acc[k].mn[i], m[i]);
+            acc[k].mx[i] = fmaxf(acc[k].mx[i], m[i]);
           }
         }
       }
@@ -113,8 +139,20 @@ __device__ __forceinline__ void accumulate_slots(const KParams& p, const FeatMap
   }
 }
 
+// Reduce slots [beg, end) of one row into acc, U slots per step.
+template <typename T, int VEC, int G, int K, int U>
+__device__ __forceinline__ void accumulate_slots(const KParams& p, const FeatMap<VEC, G, K>& fm, int beg, int end,
+                                                 const float (&bias)[K][VEC], bool has_bias, Acc<VEC> (&acc)[K]) {
+  const T* __restrict__ x = static_cast<const T*>(p.x);
+  const int* __restrict__ col = p.col;
+  const int ldx = (int)p.ldx;
+  int e = beg;
+  for (; e + U <= end; e += U) accumulate_batch<T, VEC, G, K, U, true>(x, ldx, col, fm, e, end, bias, has_bias, acc);
+  if (e < end) accumulate_batch<T, VEC, G, K, U, false>(x, ldx, col, fm, e, end, bias, has_bias, acc);
+}
+
 // mean/var/std + scalers + the S*A streaming stores of one row.
-template <typename T, int VEC, int G, int K>
+template <typename T, int VEC, int G, int K, typename Cfg>
 __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC, G, K>& fm, long long row, int deg,
                                              const Acc<VEC> (&acc)[K]) {
   const bool iso = deg == 0;
@@ -123,9 +161,15 @@ __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC
   const float lg = logf(degf + 1.0f);
   const float s_amp = __fdiv_rn(lg, p.avg_log);            // scalers.py:12-13
   const float s_att = iso ? 1.0f : __fdiv_rn(p.avg_log, lg);   // scalers.py:16-19
-  const float s_lin = __fdiv_rn(degf, p.avg_lin);          // scalers.py:22-23
-  const float s_ilin = iso ? 1.0f : __fdiv_rn(p.avg_lin, degf);  // scalers.py:26-29
+  float s_lin = 0.f, s_ilin = 0.f;
+  if (!Cfg::kStatic) {
+    s_lin = __fdiv_rn(degf, p.avg_lin);                    // scalers.py:22-23
+    s_ilin = iso ? 1.0f : __fdiv_rn(p.avg_lin, degf);      // scalers.py:26-29
+  }
   const bool zero_all = iso && (p.flags & PNA_FLAG_ZERO_ISOLATED);
+  const int nA = Cfg::kStatic ? Cfg::NA : p.nA, nS = Cfg::kStatic ? Cfg::NS : p.nS;
+  const unsigned acodes = Cfg::kStatic ? Cfg::ACODES : p.acodes, scodes = Cfg::kStatic ? Cfg::SCODES : p.scodes;
+  const int Ft = p.Ft;
   T* __restrict__ orow = static_cast<T*>(p.out) + row * p.ldo;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -145,8 +189,12 @@ __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC
       mn[i] = iso ? 0.0f : acc[k].mn[i];                                         // aggregators.py:17-22 (empty -> 0)
       mx[i] = iso ? 0.0f : acc[k].mx[i];
     }
-    for (int a = 0; a < p.nA; ++a) {
-      const unsigned ac = (p.acodes >> (4 * a)) & 15u;
+    T* __restrict__ obase = orow + fm.ooff[k];
+#pragma unroll
+    for (int a = 0; a < Cfg::NA; ++a) {
+      if (!Cfg::kStatic && a >= nA) break;
+      const unsigned ac = (acodes >> (4 * a)) & 15u;
+      if (ac == PNA_AGGR_SKIP) continue;
       float val[VEC];
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
@@ -159,10 +207,12 @@ __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC
           case PNA_AGGR_VAR: r = var[i]; break;
           default: r = sd[i]; break;
         }
-        val[i] = r;
+        val[i] = zero_all ? 0.0f : r;
       }
-      for (int s = 0; s < p.nS; ++s) {
-        const unsigned sc = (p.scodes >> (4 * s)) & 15u;
+#pragma unroll
+      for (int s = 0; s < Cfg::NS; ++s) {
+        if (!Cfg::kStatic && s >= nS) break;
+        const unsigned sc = (scodes >> (4 * s)) & 15u;
         float scale;
         switch (sc) {
           case PNA_SCALE_IDENTITY: scale = 1.0f; break;
@@ -173,8 +223,8 @@ __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC
         }
         float o[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = zero_all ? 0.0f : __fmul_rn(val[i], scale);
-        Io<T, VEC>::store(orow + fm.ooff[k] + (s * p.nA + a) * p.Ft, o);
+        for (int i = 0; i < VEC; ++i) o[i] = (sc == PNA_SCALE_IDENTITY) ? val[i] : __fmul_rn(val[i], scale);
+        Io<T, VEC>::store(obase + (s * nA + a) * Ft, o);
       }
     }
   }

@@ -1,0 +1,5 @@
+// Instantiation of the aggregation kernels for T = float, 4 element(s) per lane access.
+#include "pna_aggregate_impl.cuh"
+namespace pna {
+template int launch_typed<float, 4>(const KParams&, cudaStream_t);
+}

@@ -54,6 +54,22 @@ def avg_deg_of(ei, n, O):
     return O.avg_deg_from_histogram(torch.bincount(torch.bincount(ei[1], minlength=n)))
 
 
+def assert_matches_reference(got, x, ei, csr, O, aggrs=None, scalers=None, avg=None, tol=None):
+    """Rows below the split threshold: against the reference's fp32 op sequence (oracle), 1e-5.
+    Rows at/above it (split across warps): against the SAME formulas evaluated in float64 -- a sequential fp32 sum of
+    1e4..1e5 terms (what the reference's CPU scatter does) is itself only good to ~sqrt(d)*6e-8 relative, i.e. the fp32
+    oracle is not a 1e-5 yardstick for such rows; the exact value is."""
+    aggrs, scalers, tol = aggrs or A4, scalers or S3, tol or TOL
+    n = x.size(0)
+    want = O.simple_propagate(x, ei, aggrs, scalers, avg)
+    light = torch.bincount(ei[1], minlength=n) < csr.split_threshold
+    torch.testing.assert_close(got[light], want[light], **tol)
+    if bool((~light).any()):
+        want64 = O.simple_propagate(x.double(), ei, aggrs, scalers, avg)
+        torch.testing.assert_close(got[~light].double(), want64[~light], **tol)
+    return want, light
+
+
 # ---- CSR ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,e,hub", [(1, 0, 0), (7, 0, 0), (1, 5, 0), (100, 1000, 0), (5000, 40000, 3000), (33, 2000, 0)])
 def test_csr_is_stable_sort_by_destination(P, n, e, hub):
@@ -102,17 +118,15 @@ def test_aggregate_matches_oracle_fp32(P, O, n, e, f, hub):
     torch.manual_seed(n + f)
     x = torch.randn(n, f)
     avg = avg_deg_of(ei, n, O)
-    want = O.simple_propagate(x, ei, A4, S3, avg)
     csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
     got = P.aggregate_forward(x.to(dev()), csr, A4, S3, avg).cpu()
-    torch.testing.assert_close(got, want, **TOL)
+    want, light = assert_matches_reference(got, x, ei, csr, O, avg=avg)
     # min / max columns are order independent: exact
     fsl = slice(f, 3 * f)
     assert torch.equal(got[:, fsl], want[:, fsl])
     # rows below the split threshold follow the reference's accumulation order (edge order, unfused mul/add): the
     # mean columns are bit-identical to torch's CPU scatter path; the std columns are bit-identical to the plain-C
     # oracle (IEEE sqrtf) and within 1 ulp of torch, whose vectorised CPU sqrt is not correctly rounded
-    light = torch.bincount(ei[1], minlength=n) < csr.split_threshold
     assert torch.equal(got[light][:, :f], want[light][:, :f])
     torch.testing.assert_close(got[light][:, 3 * f:4 * f], want[light][:, 3 * f:4 * f], rtol=2.5e-7, atol=0)
     from oracle import c_oracle
@@ -131,7 +145,15 @@ def test_all_aggregators_and_scalers_any_order(P, O):
                            (["mean", "min", "max", "std"], S3)):
         want = O.simple_propagate(x, ei, aggrs, scalers, avg)
         got = P.aggregate_forward(x.to(dev()), csr, aggrs, scalers, avg).cpu()
-        torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-5)   # 'sum' of a 600-edge hub: rtol carries it
+        light = torch.bincount(ei[1], minlength=n) < csr.split_threshold
+        torch.testing.assert_close(got[light], want[light], **TOL)
+        # the split row: 'sum'/'var' of ~600 N(0,1) values cancel to O(1) while the rounding error of ANY fp32
+        # summation order is ~1e-7 * sum|x| ~ 5e-5, and 'linear' multiplies it by deg/avg ~ 50: bound it against the
+        # float64 value with that scale instead of against one particular fp32 order
+        want64 = O.simple_propagate(x.double(), ei, aggrs, scalers, avg)
+        scale = float((want64[~light].abs().max()).clamp(min=1.0))
+        assert float((got[~light].double() - want64[~light]).abs().max()) <= 2e-6 * 600 * scale
+        assert float((want[~light].double() - want64[~light]).abs().max()) <= 2e-6 * 600 * scale   # the oracle itself
 
 
 def test_isolated_rows_and_dgl_flavour(P, O):
@@ -172,7 +194,7 @@ def test_degree_1e5_hub(P, O):
     csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
     assert csr.max_degree >= 100_000
     got = P.aggregate_forward(x.to(dev()), csr, A4, S3, avg).cpu()
-    torch.testing.assert_close(got, O.simple_propagate(x, ei, A4, S3, avg), **TOL)
+    assert_matches_reference(got, x, ei, csr, O, avg=avg)
 
 
 def test_std_adversarial_identical_neighbours(P, O):
@@ -280,9 +302,8 @@ def test_config2_full_size_vs_oracle(P, O, arxiv):
     ei, x, csr = arxiv
     n = x.size(0)
     avg = avg_deg_of(ei, n, O)
-    want = O.simple_propagate(x, ei, A4, S3, avg)
     got = P.aggregate_forward(x.to(dev()), csr, A4, S3, avg).cpu()
-    torch.testing.assert_close(got, want, **TOL)
+    assert_matches_reference(got, x, ei, csr, O, avg=avg)
     assert csr.n_hubs > 0 and csr.max_degree > 5000          # the skewed destination distribution has hubs
 
 
@@ -305,12 +326,18 @@ def test_config2_size_independent_properties(P, O, arxiv):
     tot = (mean.double() * deg.double().unsqueeze(1)).sum(0)
     ref = xd.double().index_select(0, ei[0].to(dev())).sum(0)
     torch.testing.assert_close(tot, ref, rtol=1e-5, atol=2e-2)
-    # a permutation of the edge list leaves min / max untouched and mean / std within rounding
+    # a permutation of the edge list leaves min / max untouched and the mean within rounding.  The std is NOT stable
+    # under reordering at 1e-5 -- a property of the reference formula E[m^2]-E[m]^2, not of this kernel: when the
+    # variance is small against mean^2 the subtraction cancels and sqrt(.+1e-5) amplifies the rounding of the two sums
+    # by up to 1/(2*sqrt(1e-5)) = 158.  What IS stable is the variance, to fp32 rounding of E[m^2].
     p = torch.randperm(ei.size(1), generator=torch.Generator().manual_seed(1))
     csr2 = P.build_csr(ei[0][p].to(dev()), ei[1][p].to(dev()), n)
     out2 = P.aggregate_forward(xd, csr2, A4, S3, avg)
     assert torch.equal(out2[:, f:3 * f], out[:, f:3 * f])
-    torch.testing.assert_close(out2, out, **TOL)
+    torch.testing.assert_close(out2[:, :f], mean, **TOL)
+    var1, var2 = sd.double() ** 2, out2[:, 3 * f:4 * f].double() ** 2
+    msq_bound = torch.maximum(mn.abs(), mx.abs()).double() ** 2 + 1e-5
+    assert bool(((var1 - var2).abs() <= 4e-6 * msq_bound).all())
     # x -> 2x: mean/min/max double exactly (power-of-two scaling commutes with fp32 rounding)
     out3 = P.aggregate_forward(xd * 2, csr, A4, S3, avg)
     assert torch.equal(out3[:, :3 * f], out[:, :3 * f] * 2)
@@ -345,3 +372,45 @@ def test_no_cpu_fallback(P):
         P.aggregate_forward(torch.randn(2, 4), csr, A4, S3, {"log": 1.0})
     with pytest.raises(TypeError):
         P.aggregate_forward(torch.randn(2, 4, device=dev()).half(), csr, A4, S3, {"log": 1.0})
+
+
+# ---- DGL-signature and dense-adjacency drop-ins against the reference's own outputs -----------------------------
+def _graph(P, g):
+    ei = g["edge_index"]
+    return P.Graph(ei[0], ei[1], g["h"].size(0)).to(dev())
+
+
+def test_golden_dgl_simple_layer(P):
+    g = load_golden("dgl_simple")
+    lay = P.PNASimpleLayer(aggregators=g["aggregators"], scalers=g["scalers"], avg_d=g["avg_d"], **g["ctor"])
+    lay.load_state_dict(g["state_dict"])
+    lay = lay.to(dev()).eval()
+    gr = _graph(P, g)
+    with torch.no_grad():
+        agg = lay.aggregate_only(gr, g["h"].to(dev())).cpu()
+        out = lay(gr, g["h"].to(dev())).cpu()
+    torch.testing.assert_close(agg, g["aggregate"], **TOL)
+    torch.testing.assert_close(out, g["out"], **LAYER_TOL)
+
+
+@pytest.mark.parametrize("name", ["dgl_layer_t5", "dgl_layer_edge"])
+def test_golden_dgl_layer(P, name):
+    g = load_golden(name)
+    lay = P.PNALayer(aggregators=g["aggregators"], scalers=g["scalers"], avg_d=g["avg_d"], **g["ctor"])
+    lay.load_state_dict(g["state_dict"])
+    lay = lay.to(dev()).eval()
+    e = None if g["e"] is None else g["e"].to(dev())
+    with torch.no_grad():
+        out = lay(_graph(P, g), g["h"].to(dev()), e, g["snorm_n"].to(dev())).cpu()
+    torch.testing.assert_close(out, g["out"], **LAYER_TOL)
+
+
+def test_golden_dense_layer(P):
+    """The dense reference layer (imports unmodified here) on a generated graph, including its max/min axis quirk."""
+    g = load_golden("dense_k1_k2")
+    lay = P.dense.PNALayer(aggregators=A4, scalers=S3, avg_d=g["avg_d"], **g["ctor"])
+    lay.load_state_dict(g["state_dict"])
+    lay = lay.to(dev()).eval()
+    with torch.no_grad():
+        out = lay(g["h"].to(dev()), g["adj"].to(dev())).cpu()
+    torch.testing.assert_close(out, g["out"], **LAYER_TOL)
