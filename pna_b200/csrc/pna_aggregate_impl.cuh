@@ -54,6 +54,378 @@ __global__ void __launch_bounds__(kThreads, min_blocks(VEC, K)) k_rows(const KPa
   finalize_row<T, VEC, G, K, Cfg>(p, fm, row, deg, acc);
 }
 
+// ---- rows below the split threshold, tiled + software pipelined (the main kernel) ----------------------------
+// A warp owns a TILE of consecutive row slots and walks it in steps of 32/G rows (one row per lane group):
+//   * lane l loads rowptr[slot l] / rowptr[slot l + 1] once for the whole tile (coalesced); each step gets its
+//     (begin, degree) by shuffle -- no dependent rowptr load per row;
+//   * the column indices of a row are loaded by the lanes of its group in one coalesced access and handed out by
+//     shuffle -- no per-edge index load;
+//   * the loop is software pipelined: the column block of step j+1 is requested before row j is reduced, and the
+//     first U neighbour rows of step j+1 are requested BEFORE the divide/sqrt/scale/store epilogue of row j, so the
+//     gather latency of one row hides behind the arithmetic of the previous one.
+// The slot order inside a row is unchanged (sequential fp32 accumulation in CSR order).
+constexpr int kTiledThreads = 128;   // 4 warps per CTA: small CTAs retire early, keeping more warps resident
+// resident 128-thread CTAs the register allocator leaves room for: 6 -> <= 80 registers (no spills at one 128-bit
+// chunk per lane), i.e. 24 warps/SM, each with U gathers in flight underneath its epilogue
+#ifndef PNA_TILED_MINB
+#define PNA_TILED_MINB 6
+#endif
+constexpr int tiled_min_blocks(int vec, int k) { return vec * k <= 4 ? PNA_TILED_MINB : (vec * k <= 8 ? 4 : (vec * k <= 16 ? 3 : 2)); }
+
+template <typename T, int VEC, int G, int K, int U, typename Cfg, bool BIAS>
+__global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_rows_tiled(const KParams p) {
+  static_assert(U <= G && G % U == 0, "a batch must not straddle column blocks");
+  constexpr int RPW = 32 / G;                            // rows per step
+  constexpr int TR = (8 * RPW < 32) ? 8 * RPW : 32;      // row slots per tile (<= 32: one rowptr pair per lane)
+  constexpr int S = TR / RPW;                            // steps per tile
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int grp = lane / G;
+  const int gbase = grp * G;
+  const long long n_slots = p.row_ids ? p.n_row_ids : p.n_rows;
+  const long long s0 = ((long long)blockIdx.x * (kTiledThreads / 32) + (threadIdx.x >> 5)) * TR;
+  if (s0 >= n_slots) return;   // warp-uniform
+
+  // tile metadata: one slot per lane.  dg: in-degree, -1 = nothing to do here (padding slot or split row)
+  int my_row = 0, rp = 0, dg = -1;
+  if (lane < TR && s0 + lane < n_slots) {
+    my_row = p.row_ids ? __ldg(p.row_ids + s0 + lane) : (int)(s0 + lane);
+    rp = __ldg(p.rowptr + my_row);
+    dg = __ldg(p.rowptr + my_row + 1) - rp;
+    if (dg >= p.split) dg = -1;
+  }
+
+  const T* __restrict__ x = static_cast<const T*>(p.x);
+  const int* __restrict__ col = p.col;
+  const int ldx = (int)p.ldx;
+  constexpr bool has_bias = BIAS;
+  FeatMap<VEC, G, K> fm;
+  fm.init(p, gl, blockIdx.y * (G * VEC * K));
+
+  // ---- stage step 0
+  int row = __shfl_sync(FULL, my_row, grp);
+  int beg = __shfl_sync(FULL, rp, grp);
+  int deg = __shfl_sync(FULL, dg, grp);
+  int d = deg > 0 ? deg : 0;
+  int cv = (gl < d) ? (col ? __ldg(col + beg + gl) : beg + gl) : 0;
+  float bias[BIAS ? K : 1][VEC];
+  if (has_bias && deg >= 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (fm.ok[k]) Io<T, VEC>::load(static_cast<const T*>(p.bias) + (long long)row * p.ldb + fm.f[k], bias[BIAS ? k : 0]);
+  }
+  typename Io<T, VEC>::Raw raw[U][K];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int src = __shfl_sync(FULL, cv, gbase + u);
+    if (u < d) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(x + (long long)src * ldx + fm.f[k]);
+    }
+  }
+
+#pragma unroll 1
+  for (int j = 0; j < S; ++j) {
+    // ---- request metadata + first column block of step j+1
+    const int tn = (j + 1) * RPW + grp;
+    const bool more = (j + 1 < S);
+    const int rowN = __shfl_sync(FULL, my_row, tn & 31);
+    const int begN = __shfl_sync(FULL, rp, tn & 31);
+    int degN = __shfl_sync(FULL, dg, tn & 31);
+    if (!more) degN = -1;
+    const int dN = degN > 0 ? degN : 0;
+    const int cvN = (gl < dN) ? (col ? __ldg(col + begN + gl) : begN + gl) : 0;
+    float biasN[BIAS ? K : 1][VEC];
+    if (has_bias && degN >= 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (fm.ok[k]) Io<T, VEC>::load(static_cast<const T*>(p.bias) + (long long)rowN * p.ldb + fm.f[k], biasN[BIAS ? k : 0]);
+    }
+
+    // ---- reduce row j: first batch is already in flight
+    Acc<VEC> acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k].init();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u < d) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (fm.ok[k]) {
+            float m[VEC];
+            Io<T, VEC>::unpack(raw[u][k], m);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              if (has_bias) m[i] = __fadd_rn(m[i], bias[BIAS ? k : 0][i]);
+              acc[k].sum[i] = __fadd_rn(acc[k].sum[i], m[i]);
+              acc[k].sq[i] = __fadd_rn(acc[k].sq[i], __fmul_rn(m[i], m[i]));
+              acc[k].mn[i] = fminf(acc[k].mn[i], m[i]);
+              acc[k].mx[i] = fmaxf(acc[k].mx[i], m[i]);
+            }
+          }
+      }
+    }
+    // remaining slots of the longest row of this step (warp-uniform trip count; shorter rows are predicated off)
+    const int dmax = __reduce_max_sync(FULL, d);
+    for (int eb = U; eb < dmax; eb += U) {
+      if ((eb % G) == 0) cv = (eb + gl < d) ? (col ? __ldg(col + beg + eb + gl) : beg + eb + gl) : 0;
+      typename Io<T, VEC>::Raw r2[U][K];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int src = __shfl_sync(FULL, cv, gbase + ((eb + u) % G));
+        if (eb + u < d) {
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            if (fm.ok[k]) r2[u][k] = Io<T, VEC>::load_raw(x + (long long)src * ldx + fm.f[k]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (eb + u < d) {
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            if (fm.ok[k]) {
+              float m[VEC];
+              Io<T, VEC>::unpack(r2[u][k], m);
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) {
+                if (has_bias) m[i] = __fadd_rn(m[i], bias[BIAS ? k : 0][i]);
+                acc[k].sum[i] = __fadd_rn(acc[k].sum[i], m[i]);
+                acc[k].sq[i] = __fadd_rn(acc[k].sq[i], __fmul_rn(m[i], m[i]));
+                acc[k].mn[i] = fminf(acc[k].mn[i], m[i]);
+                acc[k].mx[i] = fmaxf(acc[k].mx[i], m[i]);
+              }
+            }
+        }
+      }
+    }
+
+    // ---- request the first batch of step j+1, then run the epilogue of row j underneath its latency
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int src = __shfl_sync(FULL, cvN, gbase + u);
+      if (u < dN) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(x + (long long)src * ldx + fm.f[k]);
+      }
+    }
+    if (deg >= 0) finalize_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, acc);
+
+    row = rowN; beg = begN; deg = degN; d = dN; cv = cvN;
+    if (has_bias) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) bias[BIAS ? k : 0][i] = biasN[BIAS ? k : 0][i];
+    }
+  }
+}
+
+// ---- rows below the split threshold, TMA-streamed gather (rows of >= 17 128-bit chunks: F >= 68 fp32) ----------
+// The in-edges of a tile of 16 rows form one stream of CSR slots.  The warp keeps a double-buffered ring of
+// neighbour feature rows in shared memory: all 32 lanes issue one bulk async copy (cp.async.bulk, the TMA engine's
+// 1-D path, SASS UBLKCP) each -- row x[col[slot]] -> ring slot -- completing on an mbarrier per half; while one half
+// is being reduced (ld.shared.v4, lanes = feature chunks, slot order = CSR order) the other half is in flight.
+// Gather latency is hidden by bytes in flight in shared memory instead of by registers or by more warps:
+// 24 warps x 8 KB per SM versus 24 warps x 4 x 512 B with register staging.
+constexpr int kStreamThreads = 128;
+constexpr int kStreamTile = 16;
+
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// 128-bit shared-memory load through a 32-bit shared address (no generic-address conversion in the loop)
+template <typename T, int VEC>
+__device__ __forceinline__ typename Io<T, VEC>::Raw lds_raw(unsigned addr) {
+  static_assert(sizeof(typename Io<T, VEC>::Raw) == 16, "stream path moves 128-bit chunks");
+  unsigned a, b, c, d;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+  typename Io<T, VEC>::Raw r;
+  unsigned* w = reinterpret_cast<unsigned*>(&r);
+  w[0] = a; w[1] = b; w[2] = c; w[3] = d;
+  return r;
+}
+
+template <typename T, int VEC, int K>
+struct StreamGeom {
+  static constexpr int kBlockBytes = 32 * VEC * K * (int)sizeof(T);            // bytes of one ring slot
+  static constexpr int kH = (4096 / kBlockBytes) < 4 ? 4 : ((4096 / kBlockBytes) > 32 ? 32 : (4096 / kBlockBytes));
+  static constexpr int kWarpBytes = 2 * kH * kBlockBytes;                        // two halves
+  static constexpr size_t kSmem = 128 + (size_t)(kStreamThreads / 32) * kWarpBytes;
+};
+
+template <typename T, int VEC, int K, typename Cfg, bool BIAS>
+__global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_rows_stream(const KParams p) {
+  constexpr int G = 32, TR = kStreamTile;
+  constexpr int H = StreamGeom<T, VEC, K>::kH;
+  constexpr int SLOT = StreamGeom<T, VEC, K>::kBlockBytes;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long n_slots = p.row_ids ? p.n_row_ids : p.n_rows;
+  const long long s0 = ((long long)blockIdx.x * (kStreamThreads / 32) + warp) * TR;
+  if (s0 >= n_slots) return;   // warp-uniform; no CTA-wide barrier is used below
+
+  // shared memory: [warps][2] mbarriers, then per warp a ring of 2*H slots
+  const unsigned smem0 = smem_u32(smem);
+  const unsigned bar0 = smem0 + warp * 16;
+  const unsigned ring = smem0 + 128 + warp * StreamGeom<T, VEC, K>::kWarpBytes;
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  // tile metadata: lane l < TR owns row slot l
+  int my_row = 0, rp = 0, dg = -1;
+  if (lane < TR && s0 + lane < n_slots) {
+    my_row = p.row_ids ? __ldg(p.row_ids + s0 + lane) : (int)(s0 + lane);
+    rp = __ldg(p.rowptr + my_row);
+    dg = __ldg(p.rowptr + my_row + 1) - rp;
+    if (dg >= p.split) dg = -1;
+  }
+  const int sd = dg > 0 ? dg : 0;
+  int off = sd;   // inclusive scan over lanes -> exclusive offsets of each row in the tile's slot stream
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(FULL, off, o);
+    if (lane >= o) off += t;
+  }
+  const int Te = __shfl_sync(FULL, off, 31);
+  off -= sd;
+  // contiguous fast path: consecutive rows, none split -> stream position q is CSR slot rp[0] + q
+  const int rp0 = __shfl_sync(FULL, rp, 0);
+  const bool contiguous = __all_sync(FULL, lane >= TR || s0 + lane >= n_slots || (dg >= 0 && rp == rp0 + off));
+
+  const int* __restrict__ col = p.col;
+  const long long pitch = (long long)p.ldx * (long long)sizeof(T);
+  const int fblock = blockIdx.y * (G * VEC * K);
+  const unsigned copy_bytes = (unsigned)(min(G * VEC * K, p.F - fblock) * (int)sizeof(T));
+  const unsigned char* xg = reinterpret_cast<const unsigned char*>(static_cast<const T*>(p.x) + fblock);
+  FeatMap<VEC, G, K> fm;
+  fm.init(p, lane, fblock);
+
+  // source row of stream position q (lanes >= H or q >= Te: -1)
+  auto source_of = [&](int q) -> int {
+    int slot;
+    if (contiguous) {
+      slot = rp0 + q;
+    } else {
+      int l = 0;
+#pragma unroll
+      for (int stp = TR / 2; stp > 0; stp >>= 1) {
+        const int cand = l + stp;
+        const int o = __shfl_sync(FULL, off, cand & 31);
+        if (cand < TR && o <= q) l = cand;
+      }
+      slot = __shfl_sync(FULL, rp, l) + (q - __shfl_sync(FULL, off, l));
+    }
+    if (lane >= H || q >= Te) return -1;
+    return col ? __ldg(col + slot) : slot;
+  };
+  // issue the copies of half n (positions n*H .. n*H+H-1) whose sources were fetched one step earlier
+  auto issue_half = [&](int n, int src) {
+    const int nvalid = min(H, Te - n * H);
+    const unsigned bar = bar0 + (n & 1) * 8;
+    if (lane == 0) mbar_expect_tx(bar, (unsigned)nvalid * copy_bytes);
+    if (src >= 0) bulk_g2s(ring + ((n & 1) * H + lane) * SLOT, xg + (long long)src * pitch, copy_bytes, bar);
+  };
+
+  int pend = source_of(lane);                 // sources of half 0
+  unsigned phase0 = 0, phase1 = 0;
+  if (Te > 0) {
+    issue_half(0, pend);
+    pend = source_of(H + lane);
+    if (H < Te) {
+      issue_half(1, pend);
+      pend = source_of(2 * H + lane);
+    }
+  }
+
+  const unsigned lane_off = (unsigned)lane * 16u;
+  int q = 0;   // stream position being consumed
+#pragma unroll 1
+  for (int j = 0; j < TR; ++j) {
+    const int deg = __shfl_sync(FULL, dg, j);
+    if (deg < 0) continue;    // padding slot or split row (warp-uniform)
+    const int row = __shfl_sync(FULL, my_row, j);
+    float bias[BIAS ? K : 1][VEC];
+    if (BIAS) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (fm.ok[k]) Io<T, VEC>::load(static_cast<const T*>(p.bias) + (long long)row * p.ldb + fm.f[k], bias[BIAS ? k : 0]);
+    }
+    Acc<VEC> acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k].init();
+
+    int left = deg;
+    while (left > 0) {
+      // segment = slots of this row inside the current half
+      const int inhalf = q & (H - 1);
+      const int n = q / H;     // H is a power of two
+      if (inhalf == 0) {       // entering half n: wait for its copies
+        if (n & 1) { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
+        else { mbar_wait(bar0, phase0); phase0 ^= 1; }
+      }
+      const int seg = min(left, H - inhalf);
+      unsigned sp = ring + (unsigned)((n & 1) * H + inhalf) * SLOT + lane_off;
+#pragma unroll 2
+      for (int t = 0; t < seg; ++t, sp += SLOT) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (fm.ok[k]) {
+            float m[VEC];
+            Io<T, VEC>::unpack(lds_raw<T, VEC>(sp + k * 512), m);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              if (BIAS) m[v] = __fadd_rn(m[v], bias[BIAS ? k : 0][v]);
+              acc[k].sum[v] = __fadd_rn(acc[k].sum[v], m[v]);
+              acc[k].sq[v] = __fadd_rn(acc[k].sq[v], __fmul_rn(m[v], m[v]));
+              acc[k].mn[v] = fminf(acc[k].mn[v], m[v]);
+              acc[k].mx[v] = fmaxf(acc[k].mx[v], m[v]);
+            }
+          }
+        }
+      }
+      q += seg;
+      left -= seg;
+      if ((q & (H - 1)) == 0 || q == Te) {   // half n fully consumed: refill it with half n+2
+        __syncwarp();
+        if ((n + 2) * H < Te) {
+          issue_half(n + 2, pend);
+          pend = source_of((n + 3) * H + lane);
+        }
+      }
+    }
+    finalize_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, acc);
+  }
+}
+
 // ---- hubs, pass 1: one lane group per chunk of `chunk` slots -> fp32 partials ------------------------------
 template <typename T, int VEC, int G, int K, int U>
 __global__ void __launch_bounds__(kThreads, min_blocks(VEC, K)) k_hub_chunks(const KParams p) {
@@ -198,12 +570,41 @@ static int launch_config(const KParams& p, cudaStream_t st) {
       PNA_REQUIRE(gx <= 0x7fffffffll, PNA_ERR_UNSUPPORTED, "too many rows for one launch: %lld", slots);
       const unsigned std_s = (0u) | (1u << 4) | (2u << 8);
       const bool s3 = p.nS == 3 && (p.scodes & 0xfffu) == std_s && p.nA == 4;
-      if (s3 && (p.acodes & 0xffffu) == CfgMeanMaxMinStd::ACODES)
-        k_rows<T, VEC, G, K, U, CfgMeanMaxMinStd><<<dim3((unsigned)gx, gy), kThreads, 0, st>>>(p);
-      else if (s3 && (p.acodes & 0xffffu) == CfgMeanMinMaxStd::ACODES)
-        k_rows<T, VEC, G, K, U, CfgMeanMinMaxStd><<<dim3((unsigned)gx, gy), kThreads, 0, st>>>(p);
-      else
+      const int cfg = (s3 && (p.acodes & 0xffffu) == CfgMeanMaxMinStd::ACODES) ? 1 : 0;
+      if constexpr (G == 32 && VEC > 1) {
+        // TMA-streamed gather
+        constexpr size_t smem = StreamGeom<T, VEC, K>::kSmem;
+        const long long tiles = (slots + kStreamTile - 1) / kStreamTile;
+        const long long gt = (tiles + (kStreamThreads / 32) - 1) / (kStreamThreads / 32);
+        PNA_REQUIRE(gt <= 0x7fffffffll, PNA_ERR_UNSUPPORTED, "too many rows for one launch: %lld", slots);
+        const dim3 grid((unsigned)gt, gy);
+        const bool b = p.bias != nullptr;
+#define PNA_LAUNCH_STREAM(CFG, B)                                                                                  \
+  do {                                                                                                             \
+    auto kern = k_rows_stream<T, VEC, K, CFG, B>;                                                                  \
+    if (smem > 48 * 1024) PNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, kStreamThreads, smem, st>>>(p);                                                                   \
+  } while (0)
+        if (cfg == 1 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, false);
+        else if (cfg == 1) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, true);
+        else if (!b) PNA_LAUNCH_STREAM(CfgDynamic, false);
+        else PNA_LAUNCH_STREAM(CfgDynamic, true);
+#undef PNA_LAUNCH_STREAM
+      } else if constexpr (G >= U && G % U == 0) {
+        constexpr int TR = (8 * RPW < 32) ? 8 * RPW : 32;
+        constexpr int tiles_per_block = kTiledThreads / 32;
+        const long long tiles = (slots + TR - 1) / TR;
+        const long long gt = (tiles + tiles_per_block - 1) / tiles_per_block;
+        PNA_REQUIRE(gt <= 0x7fffffffll, PNA_ERR_UNSUPPORTED, "too many rows for one launch: %lld", slots);
+        const dim3 grid((unsigned)gt, gy);
+        const bool b = p.bias != nullptr;
+        if (cfg == 1 && !b) k_rows_tiled<T, VEC, G, K, U, CfgMeanMaxMinStd, false><<<grid, kTiledThreads, 0, st>>>(p);
+        else if (cfg == 1) k_rows_tiled<T, VEC, G, K, U, CfgMeanMaxMinStd, true><<<grid, kTiledThreads, 0, st>>>(p);
+        else if (!b) k_rows_tiled<T, VEC, G, K, U, CfgDynamic, false><<<grid, kTiledThreads, 0, st>>>(p);
+        else k_rows_tiled<T, VEC, G, K, U, CfgDynamic, true><<<grid, kTiledThreads, 0, st>>>(p);
+      } else {
         k_rows<T, VEC, G, K, U, CfgDynamic><<<dim3((unsigned)gx, gy), kThreads, 0, st>>>(p);
+      }
       PNA_CUDA_TRY(cudaGetLastError());
     }
   }
