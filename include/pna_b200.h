@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNA_ABI_VERSION 3
+#define PNA_ABI_VERSION 4
 
 typedef void* pna_stream_t; /* a cudaStream_t / CUstream, passed opaquely */
 
@@ -101,7 +101,15 @@ typedef struct pna_csr {
   int64_t n_hubs;           /* out (host) */
   int64_t n_chunks;         /* out (host) */
   int32_t max_degree;       /* out (host) */
-  int32_t reserved;
+  int32_t n_part;           /* in: number of equal-cost row partitions to produce (>= 1) */
+  /* "light view": the slots of the rows BELOW the split threshold, compacted so that any contiguous range of rows
+   * is a contiguous range of slots -- what lets the streaming kernel treat a warp's rows as one slot stream.
+   * Optional: pass light_rowptr == NULL to skip it. */
+  int32_t* light_rowptr;    /* out [n_nodes+1]: prefix sum of in-degrees with split rows counted as 0 */
+  int32_t* light_deg;       /* out [n_nodes]: in-degree, -1 for split rows */
+  int32_t* light_col;       /* out [n_edges]: source node of each light slot (first n_light_edges entries valid) */
+  int32_t* part;            /* out [n_part+1]: row boundaries of partitions of equal cost (slots + 12 * rows) */
+  int64_t n_light_edges;    /* out (host) */
 } pna_csr_t;
 
 /* Bytes of device scratch pna_csr_build needs for (n_nodes, n_edges) on the current device. */
@@ -157,8 +165,17 @@ typedef struct pna_agg {
   int64_t n_hubs;
   int64_t n_chunks;
   float* hub_partials;       /* fp32 scratch [n_chunks * 4 * n_feat]; may be NULL when n_hubs == 0 */
-  const int32_t* row_ids;    /* nullable [n_row_ids]: process only these light rows (halo overlap); hubs unaffected */
+  const int32_t* row_ids;    /* nullable [n_row_ids]: process only these light rows (halo overlap); hubs unaffected.
+                                With a light view, view row i is output row row_ids[i]. */
   int64_t n_row_ids;
+  /* optional light view of the rows (pna_csr_t light_* / part; NULL = not available -> tile kernels on rowptr/col).
+   * Without row_ids it has n_rows rows; with row_ids it has n_row_ids rows. */
+  const int32_t* light_rowptr;
+  const int32_t* light_deg;
+  const int32_t* light_col;
+  const int32_t* part;
+  int32_t n_part;
+  int32_t reserved;
 } pna_agg_t;
 
 int pna_aggregate_fwd(const pna_agg_t* desc, pna_stream_t stream);

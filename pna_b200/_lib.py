@@ -22,9 +22,12 @@ CUDA_HEADERS = [os.path.join(_HERE, "csrc", n) for n in ("common.cuh", "pna_aggr
 BUILD_DIR = os.path.join(_HERE, "csrc", "build")
 
 # sm_100a only: -gencode arch=compute_100a,code=sm_100a (no PTX for other targets, no multi-arch fat binary)
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+# -fmad=false: the accumulation must round the product m*m before adding it (reference: src * src, then scatter_add);
+# ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 otherwise.  IEEE div/sqrt keep their explicit FMAs.
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC"]
 
 # status codes / enums of include/pna_b200.h
+ABI_VERSION = 4
 PNA_OK = 0
 PNA_F32, PNA_BF16 = 0, 1
 AGGR_CODES = {"sum": 0, "mean": 1, "min": 2, "max": 3, "var": 4, "std": 5, "_skip": 15}
@@ -54,7 +57,9 @@ class CsrStruct(C.Structure):
         ("hub_info", C.c_void_p), ("chunk_items", C.c_void_p),
         ("cap_hubs", C.c_int64), ("cap_chunks", C.c_int64),
         ("n_hubs", C.c_int64), ("n_chunks", C.c_int64),
-        ("max_degree", C.c_int32), ("reserved", C.c_int32),
+        ("max_degree", C.c_int32), ("n_part", C.c_int32),
+        ("light_rowptr", C.c_void_p), ("light_deg", C.c_void_p), ("light_col", C.c_void_p), ("part", C.c_void_p),
+        ("n_light_edges", C.c_int64),
     ]
 
 
@@ -76,6 +81,8 @@ class AggStruct(C.Structure):
         ("n_hubs", C.c_int64), ("n_chunks", C.c_int64),
         ("hub_partials", C.c_void_p),
         ("row_ids", C.c_void_p), ("n_row_ids", C.c_int64),
+        ("light_rowptr", C.c_void_p), ("light_deg", C.c_void_p), ("light_col", C.c_void_p), ("part", C.c_void_p),
+        ("n_part", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -149,8 +156,8 @@ def lib() -> C.CDLL:
         L.pna_gather_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_int32, C.c_void_p]
         abi = L.pna_query(QUERY_ABI_VERSION)
-        if abi != 3:
-            raise ImportError(f"{LIB_PATH} has ABI version {abi}, this package needs 3: rebuild it")
+        if abi != ABI_VERSION:
+            raise ImportError(f"{LIB_PATH} has ABI version {abi}, this package needs {ABI_VERSION}: rebuild it")
         if L.pna_query(QUERY_SIZEOF_CSR) != C.sizeof(CsrStruct) or L.pna_query(QUERY_SIZEOF_AGG) != C.sizeof(AggStruct):
             raise ImportError("ctypes struct layout does not match include/pna_b200.h: rebuild libpna_sm100.so")
         _lib = L

@@ -110,6 +110,10 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
         hub_info=_ptr(csr.hub_info) if csr.n_hubs else None, chunk_items=_ptr(csr.chunk_items) if csr.n_hubs else None,
         n_hubs=csr.n_hubs, n_chunks=csr.n_chunks, hub_partials=_ptr(partials),
         row_ids=_ptr(row_ids), n_row_ids=0 if row_ids is None else int(row_ids.numel()))
+    if row_ids is None and csr.light_rowptr is not None and N > 0:
+        # light view of the whole graph (built with the CSR): enables the TMA-streamed kernel for wide rows
+        d.light_rowptr, d.light_deg, d.part, d.n_part = _ptr(csr.light_rowptr), _ptr(csr.light_deg), _ptr(csr.part), csr.n_part
+        d.light_col = _ptr(csr.light_col) if csr.n_edges else None
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().pna_aggregate_fwd(C.byref(d), torch.cuda.current_stream(dev).cuda_stream))
     return out

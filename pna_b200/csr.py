@@ -32,6 +32,13 @@ class CSRGraph:
     n_hubs: int
     n_chunks: int
     max_degree: int
+    # light view (rows below the split threshold, slots compacted) + equal-cost row partition for the streaming kernel
+    light_rowptr: Optional[torch.Tensor] = None   # int32 [N+1]
+    light_deg: Optional[torch.Tensor] = None      # int32 [N], -1 for split rows
+    light_col: Optional[torch.Tensor] = None      # int32 [E] (first n_light_edges valid)
+    part: Optional[torch.Tensor] = None           # int32 [n_part+1]
+    n_part: int = 0
+    n_light_edges: int = 0
     _partials: dict = field(default_factory=dict, repr=False)
     _deg: Optional[torch.Tensor] = field(default=None, repr=False)
     _dst: Optional[torch.Tensor] = field(default=None, repr=False)
@@ -94,6 +101,11 @@ def build_csr(src: torch.Tensor, dst: torch.Tensor, n_nodes: int, split_threshol
         perm = torch.empty(E, dtype=torch.int32, device=dev)
         hub_info = torch.empty((cap_hubs, 4), dtype=torch.int32, device=dev)
         chunk_items = torch.empty((cap_chunks, 2), dtype=torch.int32, device=dev)
+        n_part = int(min(65536, max(1, N // 2)))
+        light_rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        light_deg = torch.empty(N, dtype=torch.int32, device=dev)
+        light_col = torch.empty(E, dtype=torch.int32, device=dev)
+        part = torch.empty(n_part + 1, dtype=torch.int32, device=dev)
         L = _lib.lib()
         nbytes = C.c_size_t(0)
         _lib.check(L.pna_csr_workspace_bytes(N, E, C.byref(nbytes)))
@@ -101,14 +113,17 @@ def build_csr(src: torch.Tensor, dst: torch.Tensor, n_nodes: int, split_threshol
         st = _lib.CsrStruct(
             n_nodes=N, n_edges=E, split_threshold=split, chunk_edges=chunk,
             rowptr=rowptr.data_ptr(), col=col.data_ptr() if E else None, perm=perm.data_ptr() if E else None,
-            hub_info=hub_info.data_ptr(), chunk_items=chunk_items.data_ptr(), cap_hubs=cap_hubs, cap_chunks=cap_chunks)
+            hub_info=hub_info.data_ptr(), chunk_items=chunk_items.data_ptr(), cap_hubs=cap_hubs, cap_chunks=cap_chunks,
+            n_part=n_part, light_rowptr=light_rowptr.data_ptr(), light_deg=light_deg.data_ptr() if N else None,
+            light_col=light_col.data_ptr() if E else None, part=part.data_ptr())
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(L.pna_csr_build(src.data_ptr() if E else None, dst.data_ptr() if E else None, C.byref(st),
                                    ws.data_ptr(), ws.numel(), stream))
     nh, nc = int(st.n_hubs), int(st.n_chunks)
     return CSRGraph(n_nodes=N, n_edges=E, rowptr=rowptr, col=col, perm=perm, split_threshold=split, chunk_edges=chunk,
                     hub_info=hub_info[:nh].clone() if nh else hub_info[:0], chunk_items=chunk_items[:nc].clone() if nc else chunk_items[:0],
-                    n_hubs=nh, n_chunks=nc, max_degree=int(st.max_degree))
+                    n_hubs=nh, n_chunks=nc, max_degree=int(st.max_degree), light_rowptr=light_rowptr, light_deg=light_deg,
+                    light_col=light_col, part=part, n_part=n_part, n_light_edges=int(st.n_light_edges))
 
 
 # ---- cache by graph identity ---------------------------------------------------------------------------------

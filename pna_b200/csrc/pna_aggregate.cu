@@ -53,6 +53,9 @@ extern "C" int pna_aggregate_fwd(const pna_agg_t* d, pna_stream_t stream) {
   p.hub_info = d->hub_info; p.chunk_items = d->chunk_items; p.n_hubs = d->n_hubs; p.n_chunks = d->n_chunks;
   p.partials = d->hub_partials;
   p.row_ids = d->row_ids; p.n_row_ids = d->row_ids ? d->n_row_ids : 0;
+  const bool view = d->light_rowptr && d->light_deg && d->part && d->n_part >= 1 && (d->light_col || !d->col);
+  p.lrowptr = view ? d->light_rowptr : nullptr; p.ldeg = d->light_deg; p.lcol = d->light_col; p.part = d->part;
+  p.n_part = d->n_part;
   PNA_REQUIRE(p.ldx < 0x7fffffffll && p.ldb < 0x7fffffffll && p.lds < 0x7fffffffll, PNA_ERR_UNSUPPORTED,
               "pna_aggregate_fwd: row pitch too large");
   PNA_REQUIRE(p.ldo >= (long long)p.T * p.Wt, PNA_ERR_BAD_ARG, "pna_aggregate_fwd: ld_out %lld < row width %lld",

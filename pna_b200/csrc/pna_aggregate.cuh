@@ -33,6 +33,7 @@ struct KParams {
   const int* hub_info; const int* chunk_items; long long n_hubs, n_chunks;
   float* partials;
   const int* row_ids; long long n_row_ids;
+  const int* lrowptr; const int* ldeg; const int* lcol; const int* part; int n_part;   // light view (nullable)
 };
 
 // Compile-time aggregator / scaler lists for the configurations the reference's configs use; Dynamic reads them from
@@ -53,12 +54,90 @@ struct CfgStatic {
 using CfgMeanMaxMinStd = CfgStatic<4, (1u) | (3u << 4) | (2u << 8) | (5u << 12), 3, (0u) | (1u << 4) | (2u << 8)>;
 using CfgMeanMinMaxStd = CfgStatic<4, (1u) | (2u << 4) | (3u << 8) | (5u << 12), 3, (0u) | (1u << 4) | (2u << 8)>;
 
+// ---- sm_100 packed fp32 arithmetic (FADD2 / FMUL2: two IEEE-rounded fp32 operations per issue slot) and the 3-input
+// FMNMX3.  Same roundings as the scalar forms -- mul.rn / add.rn are never contracted into an FMA -- so the
+// accumulation stays bit-identical to the reference's "sum += m; sumsq += m*m" sequence while the issue-slot cost of
+// one neighbour row drops from 20 to 10 instructions per 4 features.
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+// m*m per component with SCALAR multiplies: ptxas contracts mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 even with
+// -fmad=false, which would skip the rounding of the product that the reference's "src * src" performs.
+__device__ __forceinline__ float2 sqr2(float2 m) { return make_float2(__fmul_rn(m.x, m.x), __fmul_rn(m.y, m.y)); }
+__device__ __forceinline__ float min3f(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 template <int VEC>
 struct Acc {
   float sum[VEC], sq[VEC], mn[VEC], mx[VEC];
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { sum[v] = 0.f; sq[v] = 0.f; mn[v] = CUDART_INF_F; mx[v] = -CUDART_INF_F; }
+  }
+  // one neighbour row m (BIAS: m += bias first): sum += m; sq += m*m (product rounded, then added); min; max
+  template <bool BIAS>
+  __device__ __forceinline__ void add1(float (&m)[VEC], const float (&bias)[VEC]) {
+    if constexpr (VEC % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        float2 mm = make_float2(m[i], m[i + 1]);
+        if (BIAS) mm = add2_rn(mm, make_float2(bias[i], bias[i + 1]));
+        const float2 s = add2_rn(make_float2(sum[i], sum[i + 1]), mm);
+        const float2 q = add2_rn(make_float2(sq[i], sq[i + 1]), sqr2(mm));
+        sum[i] = s.x; sum[i + 1] = s.y; sq[i] = q.x; sq[i + 1] = q.y;
+        mn[i] = fminf(mn[i], mm.x); mn[i + 1] = fminf(mn[i + 1], mm.y);
+        mx[i] = fmaxf(mx[i], mm.x); mx[i + 1] = fmaxf(mx[i + 1], mm.y);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float mm = m[i];
+        if (BIAS) mm = __fadd_rn(mm, bias[i]);
+        sum[i] = __fadd_rn(sum[i], mm);
+        sq[i] = __fadd_rn(sq[i], __fmul_rn(mm, mm));
+        mn[i] = fminf(mn[i], mm);
+        mx[i] = fmaxf(mx[i], mm);
+      }
+    }
+  }
+  // two neighbour rows, a then b (slot order is kept for the sums; min/max take both at once)
+  template <bool BIAS>
+  __device__ __forceinline__ void add2(float (&a)[VEC], float (&b)[VEC], const float (&bias)[VEC]) {
+    if constexpr (VEC % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        float2 ma = make_float2(a[i], a[i + 1]), mb = make_float2(b[i], b[i + 1]);
+        if (BIAS) {
+          const float2 bb = make_float2(bias[i], bias[i + 1]);
+          ma = add2_rn(ma, bb); mb = add2_rn(mb, bb);
+        }
+        float2 s = add2_rn(make_float2(sum[i], sum[i + 1]), ma);
+        s = add2_rn(s, mb);
+        float2 q = add2_rn(make_float2(sq[i], sq[i + 1]), sqr2(ma));
+        q = add2_rn(q, sqr2(mb));
+        sum[i] = s.x; sum[i + 1] = s.y; sq[i] = q.x; sq[i + 1] = q.y;
+        mn[i] = min3f(mn[i], ma.x, mb.x); mn[i + 1] = min3f(mn[i + 1], ma.y, mb.y);
+        mx[i] = max3f(mx[i], ma.x, mb.x); mx[i + 1] = max3f(mx[i + 1], ma.y, mb.y);
+      }
+    } else {
+      add1<BIAS>(a, bias);
+      add1<BIAS>(b, bias);
+    }
   }
 };
 
@@ -117,21 +196,21 @@ __device__ __forceinline__ void accumulate_batch(const T* __restrict__ x, int ld
         if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(x + (long long)src[u] * ldx + fm.f[k]);
     }
   }
+  static_assert(U % 2 == 0, "slots are reduced two at a time");
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    if (FULL || src[u] >= 0) {
+  for (int u = 0; u < U; u += 2) {
+    const bool v0 = FULL || src[u] >= 0, v1 = FULL || src[u + 1] >= 0;
+    if (v0) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         if (fm.ok[k]) {
-          float m[VEC];
-          Io<T, VEC>::unpack(raw[u][k], m);
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) {
-            if (has_bias) m[i] = __fadd_rn(m[i], bias[k][i]);
-            acc[k].sum[i] = __fadd_rn(acc[k].sum[i], m[i]);
-            acc[k].sq[i] = __fadd_rn(acc[k].sq[i], __fmul_rn(m[i], m[i]));
-            acc[k].mn[i] = fminf(acc[k].mn[i], m[i]);
-            acc[k].mx[i] = fmaxf(acc[k].mx[i], m[i]);
+          float m0[VEC], m1[VEC];
+          Io<T, VEC>::unpack(raw[u][k], m0);
+          if (v1) {
+            Io<T, VEC>::unpack(raw[u + 1][k], m1);
+            if (has_bias) acc[k].template add2<true>(m0, m1, bias[k]); else acc[k].template add2<false>(m0, m1, bias[k]);
+          } else {
+            if (has_bias) acc[k].template add1<true>(m0, bias[k]); else acc[k].template add1<false>(m0, bias[k]);
           }
         }
       }
@@ -222,8 +301,17 @@ __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC
           default: scale = s_ilin; break;
         }
         float o[VEC];
+        if constexpr (VEC % 2 == 0) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = (sc == PNA_SCALE_IDENTITY) ? val[i] : __fmul_rn(val[i], scale);
+          for (int i = 0; i < VEC; i += 2) {
+            const float2 r = (sc == PNA_SCALE_IDENTITY) ? make_float2(val[i], val[i + 1])
+                                                        : mul2_rn(make_float2(val[i], val[i + 1]), make_float2(scale, scale));
+            o[i] = r.x; o[i + 1] = r.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) o[i] = (sc == PNA_SCALE_IDENTITY) ? val[i] : __fmul_rn(val[i], scale);
+        }
         Io<T, VEC>::store(obase + (s * nA + a) * Ft, o);
       }
     }

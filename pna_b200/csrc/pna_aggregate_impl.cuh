@@ -149,20 +149,18 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k].init();
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+    for (int u = 0; u < U; u += 2) {
       if (u < d) {
 #pragma unroll
         for (int k = 0; k < K; ++k)
           if (fm.ok[k]) {
-            float m[VEC];
-            Io<T, VEC>::unpack(raw[u][k], m);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-              if (has_bias) m[i] = __fadd_rn(m[i], bias[BIAS ? k : 0][i]);
-              acc[k].sum[i] = __fadd_rn(acc[k].sum[i], m[i]);
-              acc[k].sq[i] = __fadd_rn(acc[k].sq[i], __fmul_rn(m[i], m[i]));
-              acc[k].mn[i] = fminf(acc[k].mn[i], m[i]);
-              acc[k].mx[i] = fmaxf(acc[k].mx[i], m[i]);
+            float m0[VEC], m1[VEC];
+            Io<T, VEC>::unpack(raw[u][k], m0);
+            if (u + 1 < d) {
+              Io<T, VEC>::unpack(raw[u + 1][k], m1);
+              acc[k].template add2<BIAS>(m0, m1, bias[BIAS ? k : 0]);
+            } else {
+              acc[k].template add1<BIAS>(m0, bias[BIAS ? k : 0]);
             }
           }
       }
@@ -182,20 +180,18 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
         }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < U; u += 2) {
         if (eb + u < d) {
 #pragma unroll
           for (int k = 0; k < K; ++k)
             if (fm.ok[k]) {
-              float m[VEC];
-              Io<T, VEC>::unpack(r2[u][k], m);
-#pragma unroll
-              for (int i = 0; i < VEC; ++i) {
-                if (has_bias) m[i] = __fadd_rn(m[i], bias[BIAS ? k : 0][i]);
-                acc[k].sum[i] = __fadd_rn(acc[k].sum[i], m[i]);
-                acc[k].sq[i] = __fadd_rn(acc[k].sq[i], __fmul_rn(m[i], m[i]));
-                acc[k].mn[i] = fminf(acc[k].mn[i], m[i]);
-                acc[k].mx[i] = fmaxf(acc[k].mx[i], m[i]);
+              float m0[VEC], m1[VEC];
+              Io<T, VEC>::unpack(r2[u][k], m0);
+              if (eb + u + 1 < d) {
+                Io<T, VEC>::unpack(r2[u + 1][k], m1);
+                acc[k].template add2<BIAS>(m0, m1, bias[BIAS ? k : 0]);
+              } else {
+                acc[k].template add1<BIAS>(m0, bias[BIAS ? k : 0]);
               }
             }
         }
@@ -225,14 +221,15 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
 }
 
 // ---- rows below the split threshold, TMA-streamed gather (rows of >= 17 128-bit chunks: F >= 68 fp32) ----------
-// The in-edges of a tile of 16 rows form one stream of CSR slots.  The warp keeps a double-buffered ring of
+// Persistent warps: each owns a contiguous range of rows of the LIGHT VIEW (split rows removed, so the in-edges of
+// the range are ONE contiguous stream of slots), the ranges cut at equal-cost boundaries precomputed with the CSR.
+// The warp keeps a double-buffered ring of
 // neighbour feature rows in shared memory: all 32 lanes issue one bulk async copy (cp.async.bulk, the TMA engine's
 // 1-D path, SASS UBLKCP) each -- row x[col[slot]] -> ring slot -- completing on an mbarrier per half; while one half
 // is being reduced (ld.shared.v4, lanes = feature chunks, slot order = CSR order) the other half is in flight.
 // Gather latency is hidden by bytes in flight in shared memory instead of by registers or by more warps:
 // 24 warps x 8 KB per SM versus 24 warps x 4 x 512 B with register staging.
 constexpr int kStreamThreads = 128;
-constexpr int kStreamTile = 16;
 
 __device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -268,60 +265,71 @@ __device__ __forceinline__ typename Io<T, VEC>::Raw lds_raw(unsigned addr) {
   return r;
 }
 
+#ifndef PNA_STREAM_HALF_BYTES
+#define PNA_STREAM_HALF_BYTES 4096   // bytes of neighbour rows per ring half per warp
+#endif
 template <typename T, int VEC, int K>
 struct StreamGeom {
   static constexpr int kBlockBytes = 32 * VEC * K * (int)sizeof(T);            // bytes of one ring slot
-  static constexpr int kH = (4096 / kBlockBytes) < 4 ? 4 : ((4096 / kBlockBytes) > 32 ? 32 : (4096 / kBlockBytes));
+  static constexpr int kH = (PNA_STREAM_HALF_BYTES / kBlockBytes) < 4 ? 4 : ((PNA_STREAM_HALF_BYTES / kBlockBytes) > 32 ? 32 : (PNA_STREAM_HALF_BYTES / kBlockBytes));
   static constexpr int kWarpBytes = 2 * kH * kBlockBytes;                        // two halves
   static constexpr size_t kSmem = 128 + (size_t)(kStreamThreads / 32) * kWarpBytes;
 };
 
+// 16-byte async copy global -> shared (LDGSTS, L2-only caching) with an L2 eviction-priority hint
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src, unsigned long long policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+#ifndef PNA_STREAM_TMA
+#define PNA_STREAM_TMA 0   // 1: per-row cp.async.bulk (UBLKCP) + mbarrier; 0: per-lane 16-byte cp.async (LDGSTS) groups
+#endif
+
 template <typename T, int VEC, int K, typename Cfg, bool BIAS>
 __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_rows_stream(const KParams p) {
-  constexpr int G = 32, TR = kStreamTile;
+  constexpr int G = 32;
   constexpr int H = StreamGeom<T, VEC, K>::kH;
   constexpr int SLOT = StreamGeom<T, VEC, K>::kBlockBytes;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const long long n_slots = p.row_ids ? p.n_row_ids : p.n_rows;
-  const long long s0 = ((long long)blockIdx.x * (kStreamThreads / 32) + warp) * TR;
-  if (s0 >= n_slots) return;   // warp-uniform; no CTA-wide barrier is used below
+
+  // this warp's rows: a contiguous range of the light view, cut at equal-cost partition boundaries
+  const long long W = (long long)gridDim.x * (kStreamThreads / 32);
+  const long long w = (long long)blockIdx.x * (kStreamThreads / 32) + warp;
+  const int pa = __ldg(p.part + (int)((w * p.n_part) / W));
+  const int pb = __ldg(p.part + (int)(((w + 1) * p.n_part) / W));
+  if (pa >= pb) return;   // warp-uniform; no CTA-wide barrier is used below
+  const int Q0 = __ldg(p.lrowptr + pa);
+  const int Te = __ldg(p.lrowptr + pb) - Q0;      // length of this warp's slot stream
 
   // shared memory: [warps][2] mbarriers, then per warp a ring of 2*H slots
   const unsigned smem0 = smem_u32(smem);
   const unsigned bar0 = smem0 + warp * 16;
   const unsigned ring = smem0 + 128 + warp * StreamGeom<T, VEC, K>::kWarpBytes;
+#if PNA_STREAM_TMA
   if (lane == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+#else
+  const unsigned long long keep = l2_policy_evict_last();   // gathered rows are re-read by other destinations
+  (void)bar0;
+#endif
 
-  // tile metadata: lane l < TR owns row slot l
-  int my_row = 0, rp = 0, dg = -1;
-  if (lane < TR && s0 + lane < n_slots) {
-    my_row = p.row_ids ? __ldg(p.row_ids + s0 + lane) : (int)(s0 + lane);
-    rp = __ldg(p.rowptr + my_row);
-    dg = __ldg(p.rowptr + my_row + 1) - rp;
-    if (dg >= p.split) dg = -1;
-  }
-  const int sd = dg > 0 ? dg : 0;
-  int off = sd;   // inclusive scan over lanes -> exclusive offsets of each row in the tile's slot stream
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(FULL, off, o);
-    if (lane >= o) off += t;
-  }
-  const int Te = __shfl_sync(FULL, off, 31);
-  off -= sd;
-  // contiguous fast path: consecutive rows, none split -> stream position q is CSR slot rp[0] + q
-  const int rp0 = __shfl_sync(FULL, rp, 0);
-  const bool contiguous = __all_sync(FULL, lane >= TR || s0 + lane >= n_slots || (dg >= 0 && rp == rp0 + off));
-
-  const int* __restrict__ col = p.col;
+  const int* __restrict__ lcol = p.lcol + Q0;
   const long long pitch = (long long)p.ldx * (long long)sizeof(T);
   const int fblock = blockIdx.y * (G * VEC * K);
   const unsigned copy_bytes = (unsigned)(min(G * VEC * K, p.F - fblock) * (int)sizeof(T));
@@ -329,100 +337,135 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   FeatMap<VEC, G, K> fm;
   fm.init(p, lane, fblock);
 
-  // source row of stream position q (lanes >= H or q >= Te: -1)
-  auto source_of = [&](int q) -> int {
-    int slot;
-    if (contiguous) {
-      slot = rp0 + q;
-    } else {
-      int l = 0;
-#pragma unroll
-      for (int stp = TR / 2; stp > 0; stp >>= 1) {
-        const int cand = l + stp;
-        const int o = __shfl_sync(FULL, off, cand & 31);
-        if (cand < TR && o <= q) l = cand;
-      }
-      slot = __shfl_sync(FULL, rp, l) + (q - __shfl_sync(FULL, off, l));
-    }
-    if (lane >= H || q >= Te) return -1;
-    return col ? __ldg(col + slot) : slot;
-  };
+  // source row of stream position q for this lane (lanes >= H or q >= Te: -1)
+  auto source_of = [&](int q) -> int { return (lane < H && q < Te) ? __ldg(lcol + q) : -1; };
   // issue the copies of half n (positions n*H .. n*H+H-1) whose sources were fetched one step earlier
+#if PNA_STREAM_TMA
   auto issue_half = [&](int n, int src) {
     const int nvalid = min(H, Te - n * H);
     const unsigned bar = bar0 + (n & 1) * 8;
     if (lane == 0) mbar_expect_tx(bar, (unsigned)nvalid * copy_bytes);
     if (src >= 0) bulk_g2s(ring + ((n & 1) * H + lane) * SLOT, xg + (long long)src * pitch, copy_bytes, bar);
   };
+#else
+  // every lane copies ITS OWN 16-byte chunk(s) of each neighbour row, and later reads exactly those bytes back:
+  // completion is tracked per thread by cp.async groups, no cross-lane synchronisation is needed at all
+  const unsigned char* xl = xg + lane * 16;
+  auto issue_half = [&](int n, int src) {
+    const int nvalid = min(H, Te - n * H);
+    unsigned dst = ring + (unsigned)((n & 1) * H) * SLOT + lane * 16;
+#pragma unroll
+    for (int u = 0; u < H; ++u, dst += SLOT) {
+      const int s_u = __shfl_sync(FULL, src, u);
+      if (u < nvalid) {
+        const unsigned char* sp = xl + (long long)s_u * pitch;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (fm.ok[k]) cp_async16(dst + k * 512, sp + k * 512, keep);
+      }
+    }
+    cp_async_commit();
+  };
+#endif
 
   int pend = source_of(lane);                 // sources of half 0
   unsigned phase0 = 0, phase1 = 0;
+  (void)phase0; (void)phase1;
   if (Te > 0) {
     issue_half(0, pend);
     pend = source_of(H + lane);
+#if PNA_STREAM_TMA
     if (H < Te) {
       issue_half(1, pend);
       pend = source_of(2 * H + lane);
     }
+#else
+    issue_half(1, pend);                      // possibly empty: keeps "one group per half" so wait_group<1> is exact
+    pend = source_of(2 * H + lane);
+#endif
   }
+
+  // row metadata, 32 rows at a time, the next 32 prefetched while the current ones are reduced
+  auto load_deg = [&](int r) -> int { return (r + lane < pb) ? __ldg(p.ldeg + r + lane) : -1; };
+  auto load_rid = [&](int r) -> int { return (p.row_ids && r + lane < pb) ? __ldg(p.row_ids + r + lane) : r + lane; };
+  int dg = load_deg(pa), rid = load_rid(pa);
 
   const unsigned lane_off = (unsigned)lane * 16u;
   int q = 0;   // stream position being consumed
 #pragma unroll 1
-  for (int j = 0; j < TR; ++j) {
-    const int deg = __shfl_sync(FULL, dg, j);
-    if (deg < 0) continue;    // padding slot or split row (warp-uniform)
-    const int row = __shfl_sync(FULL, my_row, j);
-    float bias[BIAS ? K : 1][VEC];
-    if (BIAS) {
+  for (int r0 = pa; r0 < pb; r0 += 32) {
+    const int dgN = load_deg(r0 + 32), ridN = load_rid(r0 + 32);
+    const int nj = min(32, pb - r0);
+#pragma unroll 1
+    for (int j = 0; j < nj; ++j) {
+      const int deg = __shfl_sync(FULL, dg, j);
+      if (deg < 0) continue;    // split row (warp-uniform)
+      const int row = __shfl_sync(FULL, rid, j);
+      float bias[BIAS ? K : 1][VEC];
+      if (BIAS) {
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-        if (fm.ok[k]) Io<T, VEC>::load(static_cast<const T*>(p.bias) + (long long)row * p.ldb + fm.f[k], bias[BIAS ? k : 0]);
-    }
-    Acc<VEC> acc[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) acc[k].init();
-
-    int left = deg;
-    while (left > 0) {
-      // segment = slots of this row inside the current half
-      const int inhalf = q & (H - 1);
-      const int n = q / H;     // H is a power of two
-      if (inhalf == 0) {       // entering half n: wait for its copies
-        if (n & 1) { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
-        else { mbar_wait(bar0, phase0); phase0 ^= 1; }
+        for (int k = 0; k < K; ++k)
+          if (fm.ok[k]) Io<T, VEC>::load(static_cast<const T*>(p.bias) + (long long)row * p.ldb + fm.f[k], bias[BIAS ? k : 0]);
       }
-      const int seg = min(left, H - inhalf);
-      unsigned sp = ring + (unsigned)((n & 1) * H + inhalf) * SLOT + lane_off;
-#pragma unroll 2
-      for (int t = 0; t < seg; ++t, sp += SLOT) {
+      Acc<VEC> acc[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if (fm.ok[k]) {
-            float m[VEC];
-            Io<T, VEC>::unpack(lds_raw<T, VEC>(sp + k * 512), m);
+      for (int k = 0; k < K; ++k) acc[k].init();
+
+      int left = deg;
+      while (left > 0) {
+        // segment = slots of this row inside the current half
+        const int inhalf = q & (H - 1);
+        const int n = q / H;     // H is a power of two
+        if (inhalf == 0) {       // entering half n: wait for its copies
+#if PNA_STREAM_TMA
+          if (n & 1) { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
+          else { mbar_wait(bar0, phase0); phase0 ^= 1; }
+#else
+          cp_async_wait<1>();    // all groups but the newest (the other half) have landed
+#endif
+        }
+        const int seg = min(left, H - inhalf);
+        unsigned sp = ring + (unsigned)((n & 1) * H + inhalf) * SLOT + lane_off;
+        int t = 0;
+        for (; t + 2 <= seg; t += 2, sp += 2 * SLOT) {      // two slots per step: FADD2/FMUL2 + FMNMX3
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-              if (BIAS) m[v] = __fadd_rn(m[v], bias[BIAS ? k : 0][v]);
-              acc[k].sum[v] = __fadd_rn(acc[k].sum[v], m[v]);
-              acc[k].sq[v] = __fadd_rn(acc[k].sq[v], __fmul_rn(m[v], m[v]));
-              acc[k].mn[v] = fminf(acc[k].mn[v], m[v]);
-              acc[k].mx[v] = fmaxf(acc[k].mx[v], m[v]);
+          for (int k = 0; k < K; ++k) {
+            if (fm.ok[k]) {
+              float m0[VEC], m1[VEC];
+              Io<T, VEC>::unpack(lds_raw<T, VEC>(sp + k * 512), m0);
+              Io<T, VEC>::unpack(lds_raw<T, VEC>(sp + SLOT + k * 512), m1);
+              acc[k].template add2<BIAS>(m0, m1, bias[BIAS ? k : 0]);
             }
           }
         }
-      }
-      q += seg;
-      left -= seg;
-      if ((q & (H - 1)) == 0 || q == Te) {   // half n fully consumed: refill it with half n+2
-        __syncwarp();
-        if ((n + 2) * H < Te) {
-          issue_half(n + 2, pend);
+        if (t < seg) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            if (fm.ok[k]) {
+              float m0[VEC];
+              Io<T, VEC>::unpack(lds_raw<T, VEC>(sp + k * 512), m0);
+              acc[k].template add1<BIAS>(m0, bias[BIAS ? k : 0]);
+            }
+          }
+        }
+        q += seg;
+        left -= seg;
+        if ((q & (H - 1)) == 0 || q == Te) {   // half n fully consumed: refill it with half n+2
+#if PNA_STREAM_TMA
+          __syncwarp();
+          if ((n + 2) * H < Te) {
+            issue_half(n + 2, pend);
+            pend = source_of((n + 3) * H + lane);
+          }
+#else
+          issue_half(n + 2, pend);             // empty group past the end of the stream
           pend = source_of((n + 3) * H + lane);
+#endif
         }
       }
+      finalize_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, acc);
     }
-    finalize_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, acc);
+    dg = dgN; rid = ridN;
   }
 }
 
@@ -571,25 +614,34 @@ static int launch_config(const KParams& p, cudaStream_t st) {
       const unsigned std_s = (0u) | (1u << 4) | (2u << 8);
       const bool s3 = p.nS == 3 && (p.scodes & 0xfffu) == std_s && p.nA == 4;
       const int cfg = (s3 && (p.acodes & 0xffffu) == CfgMeanMaxMinStd::ACODES) ? 1 : 0;
-      if constexpr (G == 32 && VEC > 1) {
-        // TMA-streamed gather
+      if (G == 32 && VEC > 1 && p.lrowptr != nullptr && p.col != nullptr) {
+       if constexpr (G == 32 && VEC > 1) {
+        // TMA-streamed gather over the light view, persistent warps
         constexpr size_t smem = StreamGeom<T, VEC, K>::kSmem;
-        const long long tiles = (slots + kStreamTile - 1) / kStreamTile;
-        const long long gt = (tiles + (kStreamThreads / 32) - 1) / (kStreamThreads / 32);
-        PNA_REQUIRE(gt <= 0x7fffffffll, PNA_ERR_UNSUPPORTED, "too many rows for one launch: %lld", slots);
-        const dim3 grid((unsigned)gt, gy);
         const bool b = p.bias != nullptr;
 #define PNA_LAUNCH_STREAM(CFG, B)                                                                                  \
   do {                                                                                                             \
     auto kern = k_rows_stream<T, VEC, K, CFG, B>;                                                                  \
-    if (smem > 48 * 1024) PNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, kStreamThreads, smem, st>>>(p);                                                                   \
+    static int resident = 0;  /* CTAs of this kernel that fit the device (all B200s alike) */                     \
+    if (resident == 0) {                                                                                           \
+      if (smem > 48 * 1024) PNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      int dev = 0, sms = 0, nb = 0;                                                                                \
+      PNA_CUDA_TRY(cudaGetDevice(&dev));                                                                           \
+      PNA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));                             \
+      PNA_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kStreamThreads, smem));                \
+      resident = (nb > 0 ? nb : 1) * sms;                                                                          \
+    }                                                                                                              \
+    long long gxs = (slots + 8 * (kStreamThreads / 32) - 1) / (8 * (kStreamThreads / 32)); /* >= 8 rows per warp */ \
+    if (gxs > resident) gxs = resident;                                                                            \
+    if (gxs < 1) gxs = 1;                                                                                          \
+    kern<<<dim3((unsigned)gxs, gy), kStreamThreads, smem, st>>>(p);                                                \
   } while (0)
         if (cfg == 1 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, false);
         else if (cfg == 1) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, true);
         else if (!b) PNA_LAUNCH_STREAM(CfgDynamic, false);
         else PNA_LAUNCH_STREAM(CfgDynamic, true);
 #undef PNA_LAUNCH_STREAM
+       }
       } else if constexpr (G >= U && G % U == 0) {
         constexpr int TR = (8 * RPW < 32) ? 8 * RPW : 32;
         constexpr int tiles_per_block = kTiledThreads / 32;

@@ -7,6 +7,7 @@
 // which is the accumulation order of the reference's CPU scatter_add.
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace pna {
 
@@ -70,6 +71,43 @@ __global__ void k_plan_hubs(const int* __restrict__ rowptr, long long N, int spl
   }
 }
 
+// light view, step 1: deg (or -1 for split rows) and the scan input max(deg, 0); element N of the scan input is 0
+__global__ void k_light_deg(const int* __restrict__ rowptr, long long N, int split, int* __restrict__ light_deg,
+                            int* __restrict__ scan_in) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > N) return;
+  if (r == N) { scan_in[r] = 0; return; }
+  const int d = rowptr[r + 1] - rowptr[r];
+  const bool hub = d >= split;
+  light_deg[r] = hub ? -1 : d;
+  scan_in[r] = hub ? 0 : d;
+}
+
+// light view, step 2: copy the sources of the non-split rows' slots to their compacted position
+__global__ void k_light_col(const int* __restrict__ keys_sorted, const int* __restrict__ rowptr, const int* __restrict__ light_rowptr,
+                            const int* __restrict__ light_deg, const int* __restrict__ col, int E, int* __restrict__ light_col) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= E) return;
+  const int row = keys_sorted[s];
+  if (light_deg[row] < 0) return;
+  light_col[light_rowptr[row] + (s - rowptr[row])] = col[s];
+}
+
+// equal-cost partition boundaries: part[i] = smallest row r with cost(r) >= i * cost(N) / P, cost(r) = slots before r + 12 r
+__global__ void k_partition(const int* __restrict__ light_rowptr, long long N, int P, int* __restrict__ part) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > P) return;
+  if (i == P) { part[i] = (int)N; return; }
+  const long long total = (long long)light_rowptr[N] + 12ll * N;
+  const long long target = (total * i) / P;
+  long long lo = 0, hi = N;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((long long)light_rowptr[mid] + 12ll * mid < target) lo = mid + 1; else hi = mid;
+  }
+  part[i] = (int)lo;
+}
+
 static int key_bits(long long N) {
   int b = 1;
   while (b < 31 && (1ll << b) < N) ++b;
@@ -79,14 +117,17 @@ static int key_bits(long long N) {
 struct WsLayout {
   size_t keys_in, keys_out, vals_in, counters, cub_temp, cub_bytes, total;
 };
+// keys_in / vals_in are reused after the sort as the light-view scan input (needs N+1 ints), hence max(E, N+1).
 
 static int ws_layout(long long N, long long E, WsLayout* L) {
-  size_t cub_bytes = 0;
+  size_t cub_bytes = 0, scan_bytes = 0;
   const int n = (int)(E > 0 ? E : 1);
   PNA_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr,
                                                 (int*)nullptr, n, 0, key_bits(N)));
+  PNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)(N + 1)));
+  if (scan_bytes > cub_bytes) cub_bytes = scan_bytes;
   size_t off = 0;
-  const size_t eb = align_up((size_t)n * sizeof(int), 256);
+  const size_t eb = align_up((size_t)((long long)n > N + 1 ? (long long)n : N + 1) * sizeof(int), 256);
   L->keys_in = off; off += eb;
   L->keys_out = off; off += eb;
   L->vals_in = off; off += eb;
@@ -165,6 +206,24 @@ extern "C" int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* 
       PNA_CUDA_TRY(cudaGetLastError());
     }
   }
+  int n_light = 0;
+  if (csr->light_rowptr) {   // light view (optional: all four arrays or none)
+    PNA_REQUIRE(csr->light_deg && csr->part && (E == 0 || csr->light_col) && csr->n_part >= 1, PNA_ERR_BAD_ARG,
+                "pna_csr_build: light view needs light_rowptr, light_deg, light_col, part and n_part >= 1");
+    const unsigned gN = (unsigned)((N + 1 + TB - 1) / TB);
+    k_light_deg<<<gN, TB, 0, st>>>(csr->rowptr, N, csr->split_threshold, csr->light_deg, keys_in);
+    PNA_CUDA_TRY(cudaGetLastError());
+    size_t cub_bytes = L.cub_bytes;
+    PNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws + L.cub_temp, cub_bytes, (const int*)keys_in, csr->light_rowptr, (int)(N + 1), st));
+    if (E > 0) {
+      k_light_col<<<(unsigned)((E + TB - 1) / TB), TB, 0, st>>>(keys_out, csr->rowptr, csr->light_rowptr, csr->light_deg, csr->col,
+                                                                 (int)E, csr->light_col);
+      PNA_CUDA_TRY(cudaGetLastError());
+    }
+    k_partition<<<(unsigned)((csr->n_part + 1 + TB - 1) / TB), TB, 0, st>>>(csr->light_rowptr, N, csr->n_part, csr->part);
+    PNA_CUDA_TRY(cudaGetLastError());
+    PNA_CUDA_TRY(cudaMemcpyAsync(&n_light, csr->light_rowptr + N, sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
   Counters host;
   PNA_CUDA_TRY(cudaMemcpyAsync(&host, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   PNA_CUDA_TRY(cudaStreamSynchronize(st));
@@ -173,5 +232,6 @@ extern "C" int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* 
   csr->n_hubs = host.n_hubs;
   csr->n_chunks = host.n_chunks;
   csr->max_degree = host.max_degree;
+  csr->n_light_edges = n_light;
   return PNA_OK;
 }

@@ -89,6 +89,20 @@ def test_csr_is_stable_sort_by_destination(P, n, e, hub):
     assert torch.equal(info[:, 3], deg[info[:, 0]])
     assert torch.equal(info[:, 2], (deg[info[:, 0]] + csr.chunk_edges - 1) // csr.chunk_edges)
     assert csr.n_chunks == int(info[:, 2].sum())
+    # light view: split rows removed, slots compacted, equal-cost row partition
+    ldeg = torch.where(deg >= csr.split_threshold, torch.full_like(deg, -1), deg)
+    assert torch.equal(csr.light_deg.cpu().long(), ldeg)
+    lrp = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(ldeg.clamp(min=0), 0)])
+    assert torch.equal(csr.light_rowptr.cpu().long(), lrp)
+    assert csr.n_light_edges == int(lrp[-1])
+    keep = (ldeg >= 0)[ei[1][order]] if e else torch.zeros(0, dtype=torch.bool)
+    assert torch.equal(csr.light_col.cpu().long()[:csr.n_light_edges], ei[0][order][keep])
+    part = csr.part.cpu().long()
+    assert part[0] == 0 and part[-1] == n and bool((part[1:] >= part[:-1]).all()) and part.numel() == csr.n_part + 1
+    cost = lrp + 12 * torch.arange(n + 1)
+    width = (cost[part[1:]] - cost[part[:-1]]).float()
+    if csr.n_part > 4 and n > 64:
+        assert float(width.max()) <= float(cost[-1]) / csr.n_part + csr.split_threshold + 12    # balanced up to one row
     items = csr.chunk_items.cpu().long()
     for h in range(csr.n_hubs):
         first, nch = int(info[h, 1]), int(info[h, 2])
