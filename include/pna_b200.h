@@ -110,6 +110,8 @@ typedef struct pna_csr {
   int32_t* light_col;       /* out [n_edges]: source node of each light slot (first n_light_edges entries valid) */
   int32_t* part;            /* out [n_part+1]: row boundaries of partitions of equal cost (slots + 12 * rows) */
   int64_t n_light_edges;    /* out (host) */
+  int64_t n_src_nodes;      /* in: sources are validated against [0, n_src_nodes); 0 = n_nodes.  > n_nodes for the
+                               destination-partitioned multi-GPU path, where sources index [local rows ; halo rows] */
 } pna_csr_t;
 
 /* Bytes of device scratch pna_csr_build needs for (n_nodes, n_edges) on the current device. */
@@ -120,6 +122,15 @@ int pna_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, size_t* bytes);
  * out-of-range endpoints (PNA_ERR_INDEX).  Call once per graph, not per layer. */
 int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* csr, void* workspace, size_t workspace_bytes,
                   pna_stream_t stream);
+
+/* Light view restricted to the rows with row_mask[r] != 0 (NULL = all rows below the split threshold); rows outside
+ * the mask get light_deg = -1 and no slots, so the streaming kernel skips them without a row list.  Used to run the
+ * rows whose sources are all local while the halo all-to-all is in flight, then the rest.  workspace: at least
+ * pna_csr_light_view_workspace_bytes(n_nodes) bytes of device scratch. */
+int pna_csr_light_view(const int32_t* rowptr, const int32_t* col, int64_t n_nodes, int32_t split_threshold, const uint8_t* row_mask,
+                       int32_t n_part, int32_t* light_rowptr, int32_t* light_deg, int32_t* light_col, int32_t* part,
+                       void* workspace, size_t workspace_bytes, pna_stream_t stream);
+int pna_csr_light_view_workspace_bytes(int64_t n_nodes, size_t* bytes);
 
 /* ---- the aggregation ("single hand-written sm_100a CUDA kernel", north_star) ------------------------------
  * For every destination row i (PyG semantics; In(i) = slots rowptr[i]..rowptr[i+1], d = |In(i)|):
@@ -175,7 +186,12 @@ typedef struct pna_agg {
   const int32_t* light_col;
   const int32_t* part;
   int32_t n_part;
-  int32_t reserved;
+  /* destination-partitioned multi-GPU graph, gather fused with the exchange: peer_gathered[r] (DEVICE array of
+   * n_ranks device pointers) is rank r's `gathered` buffer mapped into this process (CUDA IPC / symmetric memory over
+   * NVLink); a col entry c then means row (c & ((1 << peer_shift) - 1)) of rank (c >> peer_shift).  NULL: single GPU,
+   * col indexes `gathered` directly.  All ranks use the same ld_gathered. */
+  int32_t peer_shift;
+  const void* const* peer_gathered;
 } pna_agg_t;
 
 int pna_aggregate_fwd(const pna_agg_t* desc, pna_stream_t stream);

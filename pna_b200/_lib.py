@@ -37,7 +37,7 @@ FLAG_ZERO_ISOLATED, FLAG_SKIP_LIGHT, FLAG_SKIP_HUBS = 1, 2, 4
  QUERY_MAX_FEATURES, QUERY_SIZEOF_CSR, QUERY_SIZEOF_AGG) = range(8)
 
 # every symbol the header declares (checked by tests/test_abi.py)
-EXPORTED_SYMBOLS = ("pna_csr_workspace_bytes", "pna_csr_build", "pna_aggregate_fwd", "pna_aggregate_bwd",
+EXPORTED_SYMBOLS = ("pna_csr_workspace_bytes", "pna_csr_build", "pna_csr_light_view", "pna_csr_light_view_workspace_bytes", "pna_aggregate_fwd", "pna_aggregate_bwd",
                     "pna_gather_rows", "pna_query", "pna_last_error")
 
 
@@ -59,7 +59,7 @@ class CsrStruct(C.Structure):
         ("n_hubs", C.c_int64), ("n_chunks", C.c_int64),
         ("max_degree", C.c_int32), ("n_part", C.c_int32),
         ("light_rowptr", C.c_void_p), ("light_deg", C.c_void_p), ("light_col", C.c_void_p), ("part", C.c_void_p),
-        ("n_light_edges", C.c_int64),
+        ("n_light_edges", C.c_int64), ("n_src_nodes", C.c_int64),
     ]
 
 
@@ -82,7 +82,7 @@ class AggStruct(C.Structure):
         ("hub_partials", C.c_void_p),
         ("row_ids", C.c_void_p), ("n_row_ids", C.c_int64),
         ("light_rowptr", C.c_void_p), ("light_deg", C.c_void_p), ("light_col", C.c_void_p), ("part", C.c_void_p),
-        ("n_part", C.c_int32), ("reserved", C.c_int32),
+        ("n_part", C.c_int32), ("peer_shift", C.c_int32), ("peer_gathered", C.c_void_p),
     ]
 
 
@@ -147,6 +147,11 @@ def lib() -> C.CDLL:
         L.pna_csr_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.POINTER(C.c_size_t)]
         L.pna_csr_build.restype = C.c_int
         L.pna_csr_build.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CsrStruct), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.pna_csr_light_view.restype = C.c_int
+        L.pna_csr_light_view.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.pna_csr_light_view_workspace_bytes.restype = C.c_int
+        L.pna_csr_light_view_workspace_bytes.argtypes = [C.c_int64, C.POINTER(C.c_size_t)]
         L.pna_aggregate_fwd.restype = C.c_int
         L.pna_aggregate_fwd.argtypes = [C.POINTER(AggStruct), C.c_void_p]
         L.pna_aggregate_bwd.restype = C.c_int

@@ -46,7 +46,7 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
                       self_feat: Optional[torch.Tensor] = None, self_divided: bool = True,
                       messages_in_csr_order: bool = False, zero_isolated: bool = False,
                       out: Optional[torch.Tensor] = None, row_ids: Optional[torch.Tensor] = None,
-                      skip_light: bool = False, skip_hubs: bool = False) -> torch.Tensor:
+                      skip_light: bool = False, skip_hubs: bool = False, view=None, peer=None) -> torch.Tensor:
     """Run the CUDA aggregation (no autograd).  Returns ``[N, towers * (has_self + S*A) * Ft]``.
 
     gathered : [n_src, F] rows that are gathered through ``csr.col`` (x for PNAConvSimple; V = x W_j^T + b for
@@ -110,10 +110,19 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
         hub_info=_ptr(csr.hub_info) if csr.n_hubs else None, chunk_items=_ptr(csr.chunk_items) if csr.n_hubs else None,
         n_hubs=csr.n_hubs, n_chunks=csr.n_chunks, hub_partials=_ptr(partials),
         row_ids=_ptr(row_ids), n_row_ids=0 if row_ids is None else int(row_ids.numel()))
-    if row_ids is None and csr.light_rowptr is not None and N > 0:
-        # light view of the whole graph (built with the CSR): enables the TMA-streamed kernel for wide rows
-        d.light_rowptr, d.light_deg, d.part, d.n_part = _ptr(csr.light_rowptr), _ptr(csr.light_deg), _ptr(csr.part), csr.n_part
-        d.light_col = _ptr(csr.light_col) if csr.n_edges else None
+    if view is None and row_ids is None:
+        view = csr.full_view()
+    if view is not None and row_ids is None and N > 0:
+        # light view (whole graph: built with the CSR; row subset: CSRGraph.masked_view) -> streamed-gather kernel
+        d.light_rowptr, d.light_deg, d.part, d.n_part = _ptr(view.light_rowptr), _ptr(view.light_deg), _ptr(view.part), view.n_part
+        d.light_col = _ptr(view.light_col) if csr.n_edges else None
+    if peer is not None:
+        # destination-partitioned multi-GPU graph: (int64 device tensor of per-rank row-buffer pointers, shift);
+        # col entries are owner << shift | row and remote rows are gathered over NVLink inside the kernel
+        ptr_table, shift = peer
+        if ptr_table.dtype != torch.int64 or ptr_table.device != dev:
+            raise ValueError("peer pointer table must be an int64 tensor on the same device")
+        d.peer_gathered, d.peer_shift = ptr_table.data_ptr(), int(shift)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().pna_aggregate_fwd(C.byref(d), torch.cuda.current_stream(dev).cuda_stream))
     return out

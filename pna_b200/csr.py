@@ -18,6 +18,16 @@ from . import _lib
 
 
 @dataclass
+class LightView:
+    """Slots of a subset of the rows below the split threshold, compacted (see include/pna_b200.h pna_csr_light_view)."""
+    light_rowptr: torch.Tensor    # int32 [N+1]
+    light_deg: torch.Tensor       # int32 [N], -1 = row not in this view
+    light_col: torch.Tensor       # int32 [E]
+    part: torch.Tensor            # int32 [n_part+1]
+    n_part: int
+
+
+@dataclass
 class CSRGraph:
     """In-edges of every node, segmented by destination (stable in edge order)."""
     n_nodes: int
@@ -72,14 +82,44 @@ class CSRGraph:
             self._partials[n_feat] = buf
         return buf
 
+    def masked_view(self, row_mask: torch.Tensor) -> LightView:
+        """Light view of the rows with ``row_mask != 0`` only (uint8/bool [N]); other rows are skipped by the kernel."""
+        N, dev = self.n_nodes, self.device
+        mask = row_mask.to(device=dev, dtype=torch.uint8).contiguous()
+        if mask.numel() != N:
+            raise ValueError("row_mask must have one entry per row")
+        n_part = int(min(65536, max(1, N // 2)))
+        lrp = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        ldeg = torch.empty(N, dtype=torch.int32, device=dev)
+        lcol = torch.empty(max(self.n_edges, 1), dtype=torch.int32, device=dev)
+        part = torch.empty(n_part + 1, dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            nb = C.c_size_t(0)
+            _lib.check(L.pna_csr_light_view_workspace_bytes(N, C.byref(nb)))
+            ws = torch.empty(max(int(nb.value), 256), dtype=torch.uint8, device=dev)
+            _lib.check(L.pna_csr_light_view(self.rowptr.data_ptr(), self.col.data_ptr() if self.n_edges else None, N,
+                                            self.split_threshold, mask.data_ptr() if N else None, n_part, lrp.data_ptr(),
+                                            ldeg.data_ptr() if N else None, lcol.data_ptr(), part.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        return LightView(lrp, ldeg, lcol, part, n_part)
+
+    def full_view(self) -> Optional[LightView]:
+        if self.light_rowptr is None:
+            return None
+        return LightView(self.light_rowptr, self.light_deg, self.light_col, self.part, self.n_part)
+
     def degree_histogram(self) -> torch.Tensor:
         """Histogram of in-degrees (the ``deg`` ctor argument of PNAConv; reference example.py:21-25)."""
         return torch.bincount(self.in_degree.long(), minlength=self.max_degree + 1)
 
 
 def build_csr(src: torch.Tensor, dst: torch.Tensor, n_nodes: int, split_threshold: Optional[int] = None,
-              chunk_edges: Optional[int] = None) -> CSRGraph:
-    """Build the CSR on the GPU through the C ABI.  ``src[e] -> dst[e]``; int64 CUDA tensors."""
+              chunk_edges: Optional[int] = None, n_src: Optional[int] = None) -> CSRGraph:
+    """Build the CSR on the GPU through the C ABI.  ``src[e] -> dst[e]``; int64 CUDA tensors.
+
+    ``n_src`` (default ``n_nodes``): number of source rows when they differ from the destination rows -- the
+    destination-partitioned multi-GPU path gathers from ``[local rows ; halo rows]``."""
     if not src.is_cuda or not dst.is_cuda:
         raise ValueError("pna_b200.build_csr needs CUDA tensors (there is no CPU path)")
     if src.dtype != torch.int64 or dst.dtype != torch.int64:
@@ -114,6 +154,7 @@ def build_csr(src: torch.Tensor, dst: torch.Tensor, n_nodes: int, split_threshol
             n_nodes=N, n_edges=E, split_threshold=split, chunk_edges=chunk,
             rowptr=rowptr.data_ptr(), col=col.data_ptr() if E else None, perm=perm.data_ptr() if E else None,
             hub_info=hub_info.data_ptr(), chunk_items=chunk_items.data_ptr(), cap_hubs=cap_hubs, cap_chunks=cap_chunks,
+            n_src_nodes=int(n_src) if n_src is not None else 0,
             n_part=n_part, light_rowptr=light_rowptr.data_ptr(), light_deg=light_deg.data_ptr() if N else None,
             light_col=light_col.data_ptr() if E else None, part=part.data_ptr())
         stream = torch.cuda.current_stream(dev).cuda_stream

@@ -56,6 +56,8 @@ extern "C" int pna_aggregate_fwd(const pna_agg_t* d, pna_stream_t stream) {
   const bool view = d->light_rowptr && d->light_deg && d->part && d->n_part >= 1 && (d->light_col || !d->col);
   p.lrowptr = view ? d->light_rowptr : nullptr; p.ldeg = d->light_deg; p.lcol = d->light_col; p.part = d->part;
   p.n_part = d->n_part;
+  p.peer_x = reinterpret_cast<const void* const*>(d->peer_gathered); p.peer_shift = d->peer_shift;
+  if (p.peer_x) PNA_REQUIRE(d->peer_shift >= 1 && d->peer_shift <= 30, PNA_ERR_BAD_ARG, "pna_aggregate_fwd: peer_shift out of range");
   PNA_REQUIRE(p.ldx < 0x7fffffffll && p.ldb < 0x7fffffffll && p.lds < 0x7fffffffll, PNA_ERR_UNSUPPORTED,
               "pna_aggregate_fwd: row pitch too large");
   PNA_REQUIRE(p.ldo >= (long long)p.T * p.Wt, PNA_ERR_BAD_ARG, "pna_aggregate_fwd: ld_out %lld < row width %lld",

@@ -34,7 +34,20 @@ struct KParams {
   float* partials;
   const int* row_ids; long long n_row_ids;
   const int* lrowptr; const int* ldeg; const int* lcol; const int* part; int n_part;   // light view (nullable)
+  const void* const* peer_x; int peer_shift;   // multi-GPU: x of every rank (NVLink peer pointers), col = owner << shift | row
 };
+
+// First element of gathered row `c`.  Single GPU: x + c*ldx.  Destination-partitioned multi-GPU graph: `c` encodes
+// (owner rank, row on that rank) and the row is read straight from the owner's HBM over NVLink (peer pointer) --
+// the gather and the "halo exchange" are the same load, there is no pack / all-to-all / unpack step.
+template <typename T>
+__device__ __forceinline__ const T* gathered_row(const KParams& p, int c) {
+  if (p.peer_x == nullptr) return static_cast<const T*>(p.x) + (long long)c * (int)p.ldx;
+  const unsigned owner = (unsigned)c >> p.peer_shift;
+  const int r = c & ((1 << p.peer_shift) - 1);
+  const unsigned long long base = __ldg(reinterpret_cast<const unsigned long long*>(p.peer_x) + owner);
+  return reinterpret_cast<const T*>(base) + (long long)r * (int)p.ldx;
+}
 
 // Compile-time aggregator / scaler lists for the configurations the reference's configs use; Dynamic reads them from
 // KParams.  A static list turns the epilogue into straight-line code (no uniform branches, no selects).
@@ -177,7 +190,7 @@ struct FeatMap {
 
 // One batch of U slots starting at e.  FULL: all U slots exist (no predicates in the instruction stream).
 template <typename T, int VEC, int G, int K, int U, bool FULL>
-__device__ __forceinline__ void accumulate_batch(const T* __restrict__ x, int ldx, const int* __restrict__ col,
+__device__ __forceinline__ void accumulate_batch(const KParams& p, const int* __restrict__ col,
                                                  const FeatMap<VEC, G, K>& fm, int e, int end,
                                                  const float (&bias)[K][VEC], bool has_bias, Acc<VEC> (&acc)[K]) {
   int src[U];
@@ -193,7 +206,7 @@ __device__ __forceinline__ void accumulate_batch(const T* __restrict__ x, int ld
     if (FULL || src[u] >= 0) {
 #pragma unroll
       for (int k = 0; k < K; ++k)
-        if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(x + (long long)src[u] * ldx + fm.f[k]);
+        if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(gathered_row<T>(p, src[u]) + fm.f[k]);
     }
   }
   static_assert(U % 2 == 0, "slots are reduced two at a time");
@@ -222,12 +235,10 @@ __device__ __forceinline__ void accumulate_batch(const T* __restrict__ x, int ld
 template <typename T, int VEC, int G, int K, int U>
 __device__ __forceinline__ void accumulate_slots(const KParams& p, const FeatMap<VEC, G, K>& fm, int beg, int end,
                                                  const float (&bias)[K][VEC], bool has_bias, Acc<VEC> (&acc)[K]) {
-  const T* __restrict__ x = static_cast<const T*>(p.x);
   const int* __restrict__ col = p.col;
-  const int ldx = (int)p.ldx;
   int e = beg;
-  for (; e + U <= end; e += U) accumulate_batch<T, VEC, G, K, U, true>(x, ldx, col, fm, e, end, bias, has_bias, acc);
-  if (e < end) accumulate_batch<T, VEC, G, K, U, false>(x, ldx, col, fm, e, end, bias, has_bias, acc);
+  for (; e + U <= end; e += U) accumulate_batch<T, VEC, G, K, U, true>(p, col, fm, e, end, bias, has_bias, acc);
+  if (e < end) accumulate_batch<T, VEC, G, K, U, false>(p, col, fm, e, end, bias, has_bias, acc);
 }
 
 // mean/var/std + scalers + the S*A streaming stores of one row.

@@ -94,11 +94,10 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
     rp = __ldg(p.rowptr + my_row);
     dg = __ldg(p.rowptr + my_row + 1) - rp;
     if (dg >= p.split) dg = -1;
+    if (p.ldeg && !p.row_ids) dg = __ldg(p.ldeg + my_row);   // masked view: rows outside it are skipped
   }
 
-  const T* __restrict__ x = static_cast<const T*>(p.x);
   const int* __restrict__ col = p.col;
-  const int ldx = (int)p.ldx;
   constexpr bool has_bias = BIAS;
   FeatMap<VEC, G, K> fm;
   fm.init(p, gl, blockIdx.y * (G * VEC * K));
@@ -122,7 +121,7 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
     if (u < d) {
 #pragma unroll
       for (int k = 0; k < K; ++k)
-        if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(x + (long long)src * ldx + fm.f[k]);
+        if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(gathered_row<T>(p, src) + fm.f[k]);
     }
   }
 
@@ -176,7 +175,7 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
         if (eb + u < d) {
 #pragma unroll
           for (int k = 0; k < K; ++k)
-            if (fm.ok[k]) r2[u][k] = Io<T, VEC>::load_raw(x + (long long)src * ldx + fm.f[k]);
+            if (fm.ok[k]) r2[u][k] = Io<T, VEC>::load_raw(gathered_row<T>(p, src) + fm.f[k]);
         }
       }
 #pragma unroll
@@ -205,7 +204,7 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
       if (u < dN) {
 #pragma unroll
         for (int k = 0; k < K; ++k)
-          if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(x + (long long)src * ldx + fm.f[k]);
+          if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(gathered_row<T>(p, src) + fm.f[k]);
       }
     }
     if (deg >= 0) finalize_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, acc);
@@ -330,10 +329,9 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
 #endif
 
   const int* __restrict__ lcol = p.lcol + Q0;
-  const long long pitch = (long long)p.ldx * (long long)sizeof(T);
   const int fblock = blockIdx.y * (G * VEC * K);
   const unsigned copy_bytes = (unsigned)(min(G * VEC * K, p.F - fblock) * (int)sizeof(T));
-  const unsigned char* xg = reinterpret_cast<const unsigned char*>(static_cast<const T*>(p.x) + fblock);
+  (void)copy_bytes;
   FeatMap<VEC, G, K> fm;
   fm.init(p, lane, fblock);
 
@@ -345,12 +343,12 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
     const int nvalid = min(H, Te - n * H);
     const unsigned bar = bar0 + (n & 1) * 8;
     if (lane == 0) mbar_expect_tx(bar, (unsigned)nvalid * copy_bytes);
-    if (src >= 0) bulk_g2s(ring + ((n & 1) * H + lane) * SLOT, xg + (long long)src * pitch, copy_bytes, bar);
+    if (src >= 0) bulk_g2s(ring + ((n & 1) * H + lane) * SLOT, gathered_row<T>(p, src) + fblock, copy_bytes, bar);
   };
 #else
   // every lane copies ITS OWN 16-byte chunk(s) of each neighbour row, and later reads exactly those bytes back:
   // completion is tracked per thread by cp.async groups, no cross-lane synchronisation is needed at all
-  const unsigned char* xl = xg + lane * 16;
+  const int lane_elems = fblock + lane * VEC;   // this lane's first 16-byte chunk inside a gathered row
   auto issue_half = [&](int n, int src) {
     const int nvalid = min(H, Te - n * H);
     unsigned dst = ring + (unsigned)((n & 1) * H) * SLOT + lane * 16;
@@ -358,10 +356,10 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
     for (int u = 0; u < H; ++u, dst += SLOT) {
       const int s_u = __shfl_sync(FULL, src, u);
       if (u < nvalid) {
-        const unsigned char* sp = xl + (long long)s_u * pitch;
+        const T* sp = gathered_row<T>(p, s_u) + lane_elems;
 #pragma unroll
         for (int k = 0; k < K; ++k)
-          if (fm.ok[k]) cp_async16(dst + k * 512, sp + k * 512, keep);
+          if (fm.ok[k]) cp_async16(dst + k * 512, sp + k * (32 * VEC), keep);
       }
     }
     cp_async_commit();

@@ -16,11 +16,11 @@ struct Counters {  // device-side, copied back once at the end of the build
 };
 
 __global__ void k_prepare_keys(const long long* __restrict__ src, const long long* __restrict__ dst, int E, long long N,
-                               int* __restrict__ keys, int* __restrict__ vals, Counters* ctr) {
+                               long long NS, int* __restrict__ keys, int* __restrict__ vals, Counters* ctr) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   const long long d = dst[e], s = src[e];
-  const bool bad = d < 0 || d >= N || s < 0 || s >= N;
+  const bool bad = d < 0 || d >= N || s < 0 || s >= NS;
   if (bad) atomicOr(&ctr->err, 1);
   keys[e] = bad ? 0 : (int)d;
   vals[e] = e;
@@ -71,26 +71,28 @@ __global__ void k_plan_hubs(const int* __restrict__ rowptr, long long N, int spl
   }
 }
 
-// light view, step 1: deg (or -1 for split rows) and the scan input max(deg, 0); element N of the scan input is 0
-__global__ void k_light_deg(const int* __restrict__ rowptr, long long N, int split, int* __restrict__ light_deg,
-                            int* __restrict__ scan_in) {
+// light view, step 1: deg (or -1 for split / masked-out rows) and the scan input max(deg, 0); scan_in[N] = 0
+__global__ void k_light_deg(const int* __restrict__ rowptr, long long N, int split, const unsigned char* __restrict__ mask,
+                            int* __restrict__ light_deg, int* __restrict__ scan_in) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r > N) return;
   if (r == N) { scan_in[r] = 0; return; }
   const int d = rowptr[r + 1] - rowptr[r];
-  const bool hub = d >= split;
-  light_deg[r] = hub ? -1 : d;
-  scan_in[r] = hub ? 0 : d;
+  const bool skip = d >= split || (mask && !mask[r]);
+  light_deg[r] = skip ? -1 : d;
+  scan_in[r] = skip ? 0 : d;
 }
 
-// light view, step 2: copy the sources of the non-split rows' slots to their compacted position
-__global__ void k_light_col(const int* __restrict__ keys_sorted, const int* __restrict__ rowptr, const int* __restrict__ light_rowptr,
-                            const int* __restrict__ light_deg, const int* __restrict__ col, int E, int* __restrict__ light_col) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= E) return;
-  const int row = keys_sorted[s];
-  if (light_deg[row] < 0) return;
-  light_col[light_rowptr[row] + (s - rowptr[row])] = col[s];
+// light view, step 2: one group of 8 lanes per row copies the row's sources to their compacted position
+__global__ void k_light_col(const int* __restrict__ rowptr, const int* __restrict__ light_rowptr, const int* __restrict__ light_deg,
+                            const int* __restrict__ col, long long N, int* __restrict__ light_col) {
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (r >= N) return;
+  const int d = light_deg[r];
+  if (d <= 0) return;
+  const int* __restrict__ s = col + rowptr[r];
+  int* __restrict__ t = light_col + light_rowptr[r];
+  for (int i = threadIdx.x & 7; i < d; i += 8) t[i] = s[i];
 }
 
 // equal-cost partition boundaries: part[i] = smallest row r with cost(r) >= i * cost(N) / P, cost(r) = slots before r + 12 r
@@ -138,9 +140,50 @@ static int ws_layout(long long N, long long E, WsLayout* L) {
   return PNA_OK;
 }
 
+// light view of the rows selected by `mask` (NULL = all rows below the split threshold); scan_in: N+1 ints of scratch
+static int light_view(const int* rowptr, const int* col, long long N, int split, const unsigned char* mask, int n_part,
+                      int* light_rowptr, int* light_deg, int* light_col, int* part, int* scan_in, void* cub_temp, size_t cub_bytes,
+                      cudaStream_t st) {
+  const int TB = 256;
+  k_light_deg<<<(unsigned)((N + 1 + TB - 1) / TB), TB, 0, st>>>(rowptr, N, split, mask, light_deg, scan_in);
+  PNA_CUDA_TRY(cudaGetLastError());
+  PNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, (const int*)scan_in, light_rowptr, (int)(N + 1), st));
+  if (N > 0 && col != nullptr) {
+    k_light_col<<<(unsigned)((N * 8 + TB - 1) / TB), TB, 0, st>>>(rowptr, light_rowptr, light_deg, col, N, light_col);
+    PNA_CUDA_TRY(cudaGetLastError());
+  }
+  k_partition<<<(unsigned)((n_part + 1 + TB - 1) / TB), TB, 0, st>>>(light_rowptr, N, n_part, part);
+  PNA_CUDA_TRY(cudaGetLastError());
+  return PNA_OK;
+}
+
 }  // namespace pna
 
 using namespace pna;
+
+extern "C" int pna_csr_light_view(const int32_t* rowptr, const int32_t* col, int64_t n_nodes, int32_t split_threshold,
+                                  const uint8_t* row_mask, int32_t n_part, int32_t* light_rowptr, int32_t* light_deg,
+                                  int32_t* light_col, int32_t* part, void* workspace, size_t workspace_bytes, pna_stream_t stream) {
+  PNA_REQUIRE(n_nodes >= 0 && n_nodes < 0x7fffffffll && split_threshold >= 2 && n_part >= 1, PNA_ERR_BAD_ARG,
+              "pna_csr_light_view: bad sizes");
+  PNA_REQUIRE(rowptr && light_rowptr && light_deg && part, PNA_ERR_BAD_ARG, "pna_csr_light_view: null pointer");
+  size_t scan_bytes = 0;
+  PNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)(n_nodes + 1)));
+  const size_t scan_in_bytes = align_up((size_t)(n_nodes + 1) * sizeof(int), 256);
+  const size_t need = scan_in_bytes + align_up(scan_bytes, 256);
+  PNA_REQUIRE(workspace != nullptr && workspace_bytes >= need, PNA_ERR_WORKSPACE, "pna_csr_light_view: workspace %zu bytes < required %zu", workspace_bytes, need);
+  char* ws = static_cast<char*>(workspace);
+  return light_view(rowptr, col, n_nodes, split_threshold, row_mask, n_part, light_rowptr, light_deg, light_col, part,
+                    reinterpret_cast<int*>(ws), ws + scan_in_bytes, scan_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pna_csr_light_view_workspace_bytes(int64_t n_nodes, size_t* bytes) {
+  PNA_REQUIRE(bytes != nullptr && n_nodes >= 0 && n_nodes < 0x7fffffffll, PNA_ERR_BAD_ARG, "pna_csr_light_view_workspace_bytes: bad argument");
+  size_t scan_bytes = 0;
+  PNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)(n_nodes + 1)));
+  *bytes = align_up((size_t)(n_nodes + 1) * sizeof(int), 256) + align_up(scan_bytes, 256);
+  return PNA_OK;
+}
 
 extern "C" int pna_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, size_t* bytes) {
   PNA_REQUIRE(bytes != nullptr, PNA_ERR_BAD_ARG, "pna_csr_workspace_bytes: null out pointer");
@@ -158,8 +201,10 @@ extern "C" int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* 
                              pna_stream_t stream) {
   PNA_REQUIRE(csr != nullptr, PNA_ERR_BAD_ARG, "pna_csr_build: null csr");
   const long long N = csr->n_nodes, E = csr->n_edges;
+  const long long NS = csr->n_src_nodes > 0 ? csr->n_src_nodes : N;   // bipartite: sources may include halo rows
   PNA_REQUIRE(N >= 0 && E >= 0, PNA_ERR_BAD_ARG, "pna_csr_build: negative size");
-  PNA_REQUIRE(N < 0x7fffffffll && E < 0x7fffffffll, PNA_ERR_UNSUPPORTED, "pna_csr_build: n_nodes/n_edges must be < 2^31");
+  PNA_REQUIRE(N < 0x7fffffffll && E < 0x7fffffffll && NS < 0x7fffffffll, PNA_ERR_UNSUPPORTED,
+              "pna_csr_build: n_nodes/n_src_nodes/n_edges must be < 2^31");
   PNA_REQUIRE(csr->split_threshold >= 2 && csr->chunk_edges >= 1 && csr->chunk_edges <= csr->split_threshold, PNA_ERR_BAD_ARG,
               "pna_csr_build: need split_threshold >= 2 and 1 <= chunk_edges <= split_threshold");
   PNA_REQUIRE(csr->rowptr != nullptr, PNA_ERR_BAD_ARG, "pna_csr_build: null rowptr");
@@ -186,13 +231,13 @@ extern "C" int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* 
   if (E > 0) {
     const int nE = (int)E;
     const unsigned gE = (unsigned)((E + TB - 1) / TB);
-    k_prepare_keys<<<gE, TB, 0, st>>>(reinterpret_cast<const long long*>(src), reinterpret_cast<const long long*>(dst), nE, N,
+    k_prepare_keys<<<gE, TB, 0, st>>>(reinterpret_cast<const long long*>(src), reinterpret_cast<const long long*>(dst), nE, N, NS,
                                       keys_in, vals_in, ctr);
     PNA_CUDA_TRY(cudaGetLastError());
     size_t cub_bytes = L.cub_bytes;
     PNA_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, cub_bytes, (const int*)keys_in, keys_out, (const int*)vals_in,
                                                   csr->perm, nE, 0, key_bits(N), st));
-    k_fill_col<<<gE, TB, 0, st>>>(reinterpret_cast<const long long*>(src), csr->perm, nE, N, csr->col);
+    k_fill_col<<<gE, TB, 0, st>>>(reinterpret_cast<const long long*>(src), csr->perm, nE, NS, csr->col);
     PNA_CUDA_TRY(cudaGetLastError());
   }
   {
@@ -210,24 +255,15 @@ extern "C" int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* 
   if (csr->light_rowptr) {   // light view (optional: all four arrays or none)
     PNA_REQUIRE(csr->light_deg && csr->part && (E == 0 || csr->light_col) && csr->n_part >= 1, PNA_ERR_BAD_ARG,
                 "pna_csr_build: light view needs light_rowptr, light_deg, light_col, part and n_part >= 1");
-    const unsigned gN = (unsigned)((N + 1 + TB - 1) / TB);
-    k_light_deg<<<gN, TB, 0, st>>>(csr->rowptr, N, csr->split_threshold, csr->light_deg, keys_in);
-    PNA_CUDA_TRY(cudaGetLastError());
-    size_t cub_bytes = L.cub_bytes;
-    PNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws + L.cub_temp, cub_bytes, (const int*)keys_in, csr->light_rowptr, (int)(N + 1), st));
-    if (E > 0) {
-      k_light_col<<<(unsigned)((E + TB - 1) / TB), TB, 0, st>>>(keys_out, csr->rowptr, csr->light_rowptr, csr->light_deg, csr->col,
-                                                                 (int)E, csr->light_col);
-      PNA_CUDA_TRY(cudaGetLastError());
-    }
-    k_partition<<<(unsigned)((csr->n_part + 1 + TB - 1) / TB), TB, 0, st>>>(csr->light_rowptr, N, csr->n_part, csr->part);
-    PNA_CUDA_TRY(cudaGetLastError());
+    rc = light_view(csr->rowptr, csr->col, N, csr->split_threshold, nullptr, csr->n_part, csr->light_rowptr, csr->light_deg,
+                    csr->light_col, csr->part, keys_in, ws + L.cub_temp, L.cub_bytes, st);
+    if (rc != PNA_OK) return rc;
     PNA_CUDA_TRY(cudaMemcpyAsync(&n_light, csr->light_rowptr + N, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   Counters host;
   PNA_CUDA_TRY(cudaMemcpyAsync(&host, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
   PNA_CUDA_TRY(cudaStreamSynchronize(st));
-  PNA_REQUIRE(!(host.err & 1), PNA_ERR_INDEX, "pna_csr_build: edge endpoint outside [0, %lld)", N);
+  PNA_REQUIRE(!(host.err & 1), PNA_ERR_INDEX, "pna_csr_build: edge endpoint outside dst [0, %lld) / src [0, %lld)", N, NS);
   PNA_REQUIRE(!(host.err & 2), PNA_ERR_WORKSPACE, "pna_csr_build: hub/chunk capacity exceeded");
   csr->n_hubs = host.n_hubs;
   csr->n_chunks = host.n_chunks;
