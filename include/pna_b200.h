@@ -105,11 +105,14 @@ typedef struct pna_csr {
   /* "light view": the slots of the rows BELOW the split threshold, compacted so that any contiguous range of rows
    * is a contiguous range of slots -- what lets the streaming kernel treat a warp's rows as one slot stream.
    * Optional: pass light_rowptr == NULL to skip it. */
-  int32_t* light_rowptr;    /* out [n_nodes+1]: prefix sum of in-degrees with split rows counted as 0 */
-  int32_t* light_deg;       /* out [n_nodes]: in-degree, -1 for split rows */
-  int32_t* light_col;       /* out [n_edges]: source node of each light slot (first n_light_edges entries valid) */
-  int32_t* part;            /* out [n_part+1]: row boundaries of partitions of equal cost (slots + 12 * rows) */
-  int64_t n_light_edges;    /* out (host) */
+  /* The view built here has n_nodes + cap_chunks rows: after the real rows comes one PSEUDO-ROW per chunk of the
+   * split rows (n_chunks valid), whose slots the same kernel reduces into hub_partials -- so all gathers of a layer
+   * call run in one balanced launch. */
+  int32_t* light_rowptr;    /* out [n_nodes+cap_chunks+1]: prefix sum of the view rows' slot counts (split rows: 0) */
+  int32_t* light_deg;       /* out [n_nodes+cap_chunks]: slot count of each view row, -1 = skip (split row, unused chunk row) */
+  int32_t* light_col;       /* out [n_edges]: source node of each view slot (first n_light_edges entries valid) */
+  int32_t* part;            /* out [n_part+1]: view-row boundaries of partitions of equal cost (slots + 12 * rows) */
+  int64_t n_light_edges;    /* out (host): slots in the view (= n_edges when chunk rows are included) */
   int64_t n_src_nodes;      /* in: sources are validated against [0, n_src_nodes); 0 = n_nodes.  > n_nodes for the
                                destination-partitioned multi-GPU path, where sources index [local rows ; halo rows] */
 } pna_csr_t;
@@ -186,12 +189,15 @@ typedef struct pna_agg {
   const int32_t* light_col;
   const int32_t* part;
   int32_t n_part;
+  /* view rows beyond n_rows are chunk pseudo-rows (row n_rows + c reduces chunk c into hub_partials); 0 or n_rows = none */
+  int64_t n_view_rows;
   /* destination-partitioned multi-GPU graph, gather fused with the exchange: peer_gathered[r] (DEVICE array of
    * n_ranks device pointers) is rank r's `gathered` buffer mapped into this process (CUDA IPC / symmetric memory over
    * NVLink); a col entry c then means row (c & ((1 << peer_shift) - 1)) of rank (c >> peer_shift).  NULL: single GPU,
    * col indexes `gathered` directly.  All ranks use the same ld_gathered. */
-  int32_t peer_shift;
   const void* const* peer_gathered;
+  int32_t peer_shift;
+  int32_t reserved;
 } pna_agg_t;
 
 int pna_aggregate_fwd(const pna_agg_t* desc, pna_stream_t stream);

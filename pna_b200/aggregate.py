@@ -116,6 +116,7 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
         # light view (whole graph: built with the CSR; row subset: CSRGraph.masked_view) -> streamed-gather kernel
         d.light_rowptr, d.light_deg, d.part, d.n_part = _ptr(view.light_rowptr), _ptr(view.light_deg), _ptr(view.part), view.n_part
         d.light_col = _ptr(view.light_col) if csr.n_edges else None
+        d.n_view_rows = view.n_view_rows or N
     if peer is not None:
         # destination-partitioned multi-GPU graph: (int64 device tensor of per-rank row-buffer pointers, shift);
         # col entries are owner << shift | row and remote rows are gathered over NVLink inside the kernel

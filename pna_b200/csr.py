@@ -25,6 +25,7 @@ class LightView:
     light_col: torch.Tensor       # int32 [E]
     part: torch.Tensor            # int32 [n_part+1]
     n_part: int
+    n_view_rows: int = 0          # > n_nodes: the view ends with one pseudo-row per chunk of the split rows
 
 
 @dataclass
@@ -102,12 +103,12 @@ class CSRGraph:
                                             self.split_threshold, mask.data_ptr() if N else None, n_part, lrp.data_ptr(),
                                             ldeg.data_ptr() if N else None, lcol.data_ptr(), part.data_ptr(), ws.data_ptr(),
                                             ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
-        return LightView(lrp, ldeg, lcol, part, n_part)
+        return LightView(lrp, ldeg, lcol, part, n_part, N)
 
     def full_view(self) -> Optional[LightView]:
         if self.light_rowptr is None:
             return None
-        return LightView(self.light_rowptr, self.light_deg, self.light_col, self.part, self.n_part)
+        return LightView(self.light_rowptr, self.light_deg, self.light_col, self.part, self.n_part, self.n_nodes + self.n_chunks)
 
     def degree_histogram(self) -> torch.Tensor:
         """Histogram of in-degrees (the ``deg`` ctor argument of PNAConv; reference example.py:21-25)."""
@@ -142,8 +143,8 @@ def build_csr(src: torch.Tensor, dst: torch.Tensor, n_nodes: int, split_threshol
         hub_info = torch.empty((cap_hubs, 4), dtype=torch.int32, device=dev)
         chunk_items = torch.empty((cap_chunks, 2), dtype=torch.int32, device=dev)
         n_part = int(min(65536, max(1, N // 2)))
-        light_rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
-        light_deg = torch.empty(N, dtype=torch.int32, device=dev)
+        light_rowptr = torch.empty(N + cap_chunks + 1, dtype=torch.int32, device=dev)   # real rows + chunk pseudo-rows
+        light_deg = torch.empty(N + cap_chunks, dtype=torch.int32, device=dev)
         light_col = torch.empty(E, dtype=torch.int32, device=dev)
         part = torch.empty(n_part + 1, dtype=torch.int32, device=dev)
         L = _lib.lib()
@@ -155,7 +156,7 @@ def build_csr(src: torch.Tensor, dst: torch.Tensor, n_nodes: int, split_threshol
             rowptr=rowptr.data_ptr(), col=col.data_ptr() if E else None, perm=perm.data_ptr() if E else None,
             hub_info=hub_info.data_ptr(), chunk_items=chunk_items.data_ptr(), cap_hubs=cap_hubs, cap_chunks=cap_chunks,
             n_src_nodes=int(n_src) if n_src is not None else 0,
-            n_part=n_part, light_rowptr=light_rowptr.data_ptr(), light_deg=light_deg.data_ptr() if N else None,
+            n_part=n_part, light_rowptr=light_rowptr.data_ptr(), light_deg=light_deg.data_ptr(),
             light_col=light_col.data_ptr() if E else None, part=part.data_ptr())
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(L.pna_csr_build(src.data_ptr() if E else None, dst.data_ptr() if E else None, C.byref(st),

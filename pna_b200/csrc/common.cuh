@@ -32,6 +32,25 @@ int cuda_fail(cudaError_t e, const char* what);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- order of the rows of a "view" ------------------------------------------------------------------------------
+// A view lists the N real rows and, interleaved evenly among them, the M chunk pseudo-rows of the split rows (one
+// chunk row after every N/M real rows), so that every warp's contiguous range of view rows mixes epilogue-heavy real
+// rows with gather-heavy chunk rows.  view_to_row returns the real row index, or N + c for chunk c.
+struct ViewMap {
+  long long N;
+  int M;
+  __host__ __device__ long long rows() const { return N + M; }
+  __host__ __device__ long long to_row(long long v) const {
+    if (M <= 0) return v;
+    const long long s = N / M, g = s + 1;
+    if (v < g * M) {
+      const long long b = v / g, o = v - b * g;
+      return o < s ? b * s + o : N + b;
+    }
+    return s * M + (v - g * M);
+  }
+};
+
 // ---- element load/store with fp32 math -------------------------------------------------------------------
 // Gathered rows go through the read-only path (ld.global.nc); the [N, S*A*F] result is written once and never
 // re-read by this library, so it is stored with the streaming (evict-first) policy to keep source rows in L2.

@@ -53,9 +53,16 @@ extern "C" int pna_aggregate_fwd(const pna_agg_t* d, pna_stream_t stream) {
   p.hub_info = d->hub_info; p.chunk_items = d->chunk_items; p.n_hubs = d->n_hubs; p.n_chunks = d->n_chunks;
   p.partials = d->hub_partials;
   p.row_ids = d->row_ids; p.n_row_ids = d->row_ids ? d->n_row_ids : 0;
-  const bool view = d->light_rowptr && d->light_deg && d->part && d->n_part >= 1 && (d->light_col || !d->col);
-  p.lrowptr = view ? d->light_rowptr : nullptr; p.ldeg = d->light_deg; p.lcol = d->light_col; p.part = d->part;
+  // a view that contains chunk pseudo-rows cannot be used when the split rows are to be skipped
+  const bool view = d->light_rowptr && d->light_deg && d->part && d->n_part >= 1 && (d->light_col || !d->col) &&
+                    !(d->n_view_rows > d->n_rows && ((d->flags & PNA_FLAG_SKIP_HUBS) || d->row_ids));
+  p.lrowptr = view ? d->light_rowptr : nullptr; p.ldeg = view ? d->light_deg : nullptr; p.lcol = d->light_col; p.part = d->part;
   p.n_part = d->n_part;
+  // chunk pseudo-rows are only usable when the split rows are to be processed in this call
+  p.n_view_rows = (view && d->n_view_rows > d->n_rows && !(d->flags & PNA_FLAG_SKIP_HUBS) && d->n_hubs > 0 && !d->row_ids)
+                      ? d->n_view_rows : d->n_rows;
+  PNA_REQUIRE(p.n_view_rows == d->n_rows || d->n_view_rows == d->n_rows + d->n_chunks, PNA_ERR_BAD_ARG,
+              "pna_aggregate_fwd: n_view_rows must be n_rows + n_chunks");
   p.peer_x = reinterpret_cast<const void* const*>(d->peer_gathered); p.peer_shift = d->peer_shift;
   if (p.peer_x) PNA_REQUIRE(d->peer_shift >= 1 && d->peer_shift <= 30, PNA_ERR_BAD_ARG, "pna_aggregate_fwd: peer_shift out of range");
   PNA_REQUIRE(p.ldx < 0x7fffffffll && p.ldb < 0x7fffffffll && p.lds < 0x7fffffffll, PNA_ERR_UNSUPPORTED,

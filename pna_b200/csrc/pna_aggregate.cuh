@@ -34,6 +34,7 @@ struct KParams {
   float* partials;
   const int* row_ids; long long n_row_ids;
   const int* lrowptr; const int* ldeg; const int* lcol; const int* part; int n_part;   // light view (nullable)
+  long long n_view_rows;   // > n_rows: view rows n_rows + c are chunk pseudo-rows reduced into partials[c]
   const void* const* peer_x; int peer_shift;   // multi-GPU: x of every rank (NVLink peer pointers), col = owner << shift | row
 };
 

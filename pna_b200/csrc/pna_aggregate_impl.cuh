@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
     rp = __ldg(p.rowptr + my_row);
     dg = __ldg(p.rowptr + my_row + 1) - rp;
     if (dg >= p.split) dg = -1;
-    if (p.ldeg && !p.row_ids) dg = __ldg(p.ldeg + my_row);   // masked view: rows outside it are skipped
+    // masked view in row order (no chunk pseudo-rows): rows outside it are skipped
+    if (p.ldeg && !p.row_ids && p.n_view_rows == p.n_rows) dg = __ldg(p.ldeg + my_row);
   }
 
   const int* __restrict__ col = p.col;
@@ -385,7 +386,11 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
 
   // row metadata, 32 rows at a time, the next 32 prefetched while the current ones are reduced
   auto load_deg = [&](int r) -> int { return (r + lane < pb) ? __ldg(p.ldeg + r + lane) : -1; };
-  auto load_rid = [&](int r) -> int { return (p.row_ids && r + lane < pb) ? __ldg(p.row_ids + r + lane) : r + lane; };
+  const ViewMap vmap = {p.n_rows, (int)(p.n_view_rows - p.n_rows)};   // M > 0: chunk pseudo-rows interleaved in the view
+  auto load_rid = [&](int r) -> int {
+    if (p.row_ids) return (r + lane < pb) ? __ldg(p.row_ids + r + lane) : 0;
+    return (int)vmap.to_row(r + lane);
+  };
   int dg = load_deg(pa), rid = load_rid(pa);
 
   const unsigned lane_off = (unsigned)lane * 16u;
@@ -399,11 +404,14 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
       const int deg = __shfl_sync(FULL, dg, j);
       if (deg < 0) continue;    // split row (warp-uniform)
       const int row = __shfl_sync(FULL, rid, j);
+      const bool chunk_row = row >= p.n_rows;      // pseudo-row: one chunk of a split row, reduced into partials
       float bias[BIAS ? K : 1][VEC];
       if (BIAS) {
+        long long brow = row;
+        if (chunk_row) brow = __ldg(p.hub_info + 4 * __ldg(p.chunk_items + 2 * (row - (int)p.n_rows)));
 #pragma unroll
         for (int k = 0; k < K; ++k)
-          if (fm.ok[k]) Io<T, VEC>::load(static_cast<const T*>(p.bias) + (long long)row * p.ldb + fm.f[k], bias[BIAS ? k : 0]);
+          if (fm.ok[k]) Io<T, VEC>::load(static_cast<const T*>(p.bias) + brow * p.ldb + fm.f[k], bias[BIAS ? k : 0]);
       }
       Acc<VEC> acc[K];
 #pragma unroll
@@ -461,7 +469,19 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
 #endif
         }
       }
-      finalize_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, acc);
+      if (!chunk_row) {
+        finalize_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, acc);
+      } else {
+        float* __restrict__ part = p.partials + (long long)(row - (int)p.n_rows) * 4ll * p.F;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (!fm.ok[k]) continue;
+          store_f32<VEC>(part + 0ll * p.F + fm.f[k], acc[k].sum);
+          store_f32<VEC>(part + 1ll * p.F + fm.f[k], acc[k].sq);
+          store_f32<VEC>(part + 2ll * p.F + fm.f[k], acc[k].mn);
+          store_f32<VEC>(part + 3ll * p.F + fm.f[k], acc[k].mx);
+        }
+      }
     }
     dg = dgN; rid = ridN;
   }
@@ -604,6 +624,7 @@ static int launch_config(const KParams& p, cudaStream_t st) {
   constexpr int RPW = 32 / G;
   constexpr int per_block = (kThreads / 32) * RPW;
   const unsigned gy = (unsigned)((p.F + G * VEC * K - 1) / (G * VEC * K));
+  bool chunks_in_stream = false;   // the streamed kernel also reduced the chunks of the split rows
   if (!(p.flags & PNA_FLAG_SKIP_LIGHT)) {
     const long long slots = p.row_ids ? p.n_row_ids : p.n_rows;
     if (slots > 0) {
@@ -638,6 +659,7 @@ static int launch_config(const KParams& p, cudaStream_t st) {
         else if (cfg == 1) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, true);
         else if (!b) PNA_LAUNCH_STREAM(CfgDynamic, false);
         else PNA_LAUNCH_STREAM(CfgDynamic, true);
+        chunks_in_stream = p.n_view_rows > p.n_rows;
 #undef PNA_LAUNCH_STREAM
        }
       } else if constexpr (G >= U && G % U == 0) {
@@ -659,9 +681,11 @@ static int launch_config(const KParams& p, cudaStream_t st) {
     }
   }
   if (!(p.flags & PNA_FLAG_SKIP_HUBS) && p.n_hubs > 0) {
-    const long long gc = (p.n_chunks + per_block - 1) / per_block;
-    k_hub_chunks<T, VEC, G, K, U><<<dim3((unsigned)gc, gy), kThreads, 0, st>>>(p);
-    PNA_CUDA_TRY(cudaGetLastError());
+    if (!chunks_in_stream) {
+      const long long gc = (p.n_chunks + per_block - 1) / per_block;
+      k_hub_chunks<T, VEC, G, K, U><<<dim3((unsigned)gc, gy), kThreads, 0, st>>>(p);
+      PNA_CUDA_TRY(cudaGetLastError());
+    }
     k_hub_finalize<T, VEC, G, K><<<dim3((unsigned)p.n_hubs, gy), kFinGroups * G, 0, st>>>(p);
     PNA_CUDA_TRY(cudaGetLastError());
   }

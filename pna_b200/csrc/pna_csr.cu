@@ -71,38 +71,74 @@ __global__ void k_plan_hubs(const int* __restrict__ rowptr, long long N, int spl
   }
 }
 
-// light view, step 1: deg (or -1 for split / masked-out rows) and the scan input max(deg, 0); scan_in[N] = 0
-__global__ void k_light_deg(const int* __restrict__ rowptr, long long N, int split, const unsigned char* __restrict__ mask,
-                            int* __restrict__ light_deg, int* __restrict__ scan_in) {
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r > N) return;
-  if (r == N) { scan_in[r] = 0; return; }
-  const int d = rowptr[r + 1] - rowptr[r];
-  const bool skip = d >= split || (mask && !mask[r]);
-  light_deg[r] = skip ? -1 : d;
-  scan_in[r] = skip ? 0 : d;
+// A view has N real rows followed by (optionally) one pseudo-row per chunk of a split row: the chunk's slots are
+// reduced by the same streaming kernel into fp32 partials instead of a finished output row.
+struct ChunkRows {
+  const int* hub_info;     // [4*h]: row, first chunk, n chunks, degree
+  const int* chunk_items;  // [2*c]: hub, chunk-in-hub
+  const int* n_chunks;     // device counter (number of valid chunk rows), NULL = no chunk rows in this view
+  int chunk;               // slots per chunk
+};
+
+__device__ __forceinline__ int chunk_row_slots(const ChunkRows& cr, int c, int* first_slot_of_row, const int* rowptr) {
+  const int h = cr.chunk_items[2 * c], j = cr.chunk_items[2 * c + 1];
+  const int row = cr.hub_info[4 * h], deg = cr.hub_info[4 * h + 3];
+  if (first_slot_of_row) *first_slot_of_row = rowptr[row] + j * cr.chunk;
+  return min(cr.chunk, deg - j * cr.chunk);
 }
 
-// light view, step 2: one group of 8 lanes per row copies the row's sources to their compacted position
+// light view, step 1: deg (or -1 for split / masked-out rows) and the scan input max(deg, 0); scan_in[NV] = 0
+__global__ void k_light_deg(const int* __restrict__ rowptr, long long N, long long NV, int split, const unsigned char* __restrict__ mask,
+                            ChunkRows cr, int* __restrict__ light_deg, int* __restrict__ scan_in) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > NV) return;
+  if (v == NV) { scan_in[v] = 0; return; }
+  const int M = cr.n_chunks ? *cr.n_chunks : 0;
+  const ViewMap vm = {N, M};
+  if (v >= vm.rows()) { light_deg[v] = -1; scan_in[v] = 0; return; }   // unused capacity
+  const long long r = vm.to_row(v);
+  int d;
+  bool skip;
+  if (r < N) {
+    d = rowptr[r + 1] - rowptr[r];
+    skip = d >= split || (mask && !mask[r]);
+  } else {
+    const int c = (int)(r - N);
+    skip = false;
+    d = chunk_row_slots(cr, c, nullptr, rowptr);
+  }
+  light_deg[v] = skip ? -1 : d;
+  scan_in[v] = skip ? 0 : d;
+}
+
+// light view, step 2: one group of 8 lanes per view row copies the row's sources to their compacted position
 __global__ void k_light_col(const int* __restrict__ rowptr, const int* __restrict__ light_rowptr, const int* __restrict__ light_deg,
-                            const int* __restrict__ col, long long N, int* __restrict__ light_col) {
-  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  if (r >= N) return;
-  const int d = light_deg[r];
+                            const int* __restrict__ col, long long N, long long NV, ChunkRows cr, int* __restrict__ light_col) {
+  const long long v = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (v >= NV) return;
+  const int d = light_deg[v];
   if (d <= 0) return;
-  const int* __restrict__ s = col + rowptr[r];
-  int* __restrict__ t = light_col + light_rowptr[r];
+  const ViewMap vm = {N, cr.n_chunks ? *cr.n_chunks : 0};
+  const long long r = vm.to_row(v);
+  int first;
+  if (r < N) first = rowptr[r];
+  else chunk_row_slots(cr, (int)(r - N), &first, rowptr);
+  const int* __restrict__ s = col + first;
+  int* __restrict__ t = light_col + light_rowptr[v];
   for (int i = threadIdx.x & 7; i < d; i += 8) t[i] = s[i];
 }
 
-// equal-cost partition boundaries: part[i] = smallest row r with cost(r) >= i * cost(N) / P, cost(r) = slots before r + 12 r
-__global__ void k_partition(const int* __restrict__ light_rowptr, long long N, int P, int* __restrict__ part) {
+// equal-cost partition boundaries over the NV' = N + n_chunks valid view rows:
+// part[i] = smallest row r with cost(r) >= i * cost(NV') / P, cost(r) = slots before r + 12 r
+__global__ void k_partition(const int* __restrict__ light_rowptr, long long N, const int* __restrict__ n_chunks, int P,
+                            int* __restrict__ part) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > P) return;
-  if (i == P) { part[i] = (int)N; return; }
-  const long long total = (long long)light_rowptr[N] + 12ll * N;
+  const long long NV = N + (n_chunks ? *n_chunks : 0);
+  if (i == P) { part[i] = (int)NV; return; }
+  const long long total = (long long)light_rowptr[NV] + 12ll * NV;
   const long long target = (total * i) / P;
-  long long lo = 0, hi = N;
+  long long lo = 0, hi = NV;
   while (lo < hi) {
     const long long mid = (lo + hi) >> 1;
     if ((long long)light_rowptr[mid] + 12ll * mid < target) lo = mid + 1; else hi = mid;
@@ -126,10 +162,12 @@ static int ws_layout(long long N, long long E, WsLayout* L) {
   const int n = (int)(E > 0 ? E : 1);
   PNA_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr,
                                                 (int*)nullptr, n, 0, key_bits(N)));
-  PNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)(N + 1)));
+  const long long scan_n = N + 2 * E + 4;   // view rows: N real + up to E/chunk + E/split + 2 chunk rows, + 1
+  PNA_REQUIRE(scan_n < 0x7fffffffll, PNA_ERR_UNSUPPORTED, "pna_csr_build: graph too large for the int32 view scan");
+  PNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)scan_n));
   if (scan_bytes > cub_bytes) cub_bytes = scan_bytes;
   size_t off = 0;
-  const size_t eb = align_up((size_t)((long long)n > N + 1 ? (long long)n : N + 1) * sizeof(int), 256);
+  const size_t eb = align_up((size_t)((long long)n > scan_n ? (long long)n : scan_n) * sizeof(int), 256);
   L->keys_in = off; off += eb;
   L->keys_out = off; off += eb;
   L->vals_in = off; off += eb;
@@ -140,19 +178,20 @@ static int ws_layout(long long N, long long E, WsLayout* L) {
   return PNA_OK;
 }
 
-// light view of the rows selected by `mask` (NULL = all rows below the split threshold); scan_in: N+1 ints of scratch
-static int light_view(const int* rowptr, const int* col, long long N, int split, const unsigned char* mask, int n_part,
-                      int* light_rowptr, int* light_deg, int* light_col, int* part, int* scan_in, void* cub_temp, size_t cub_bytes,
-                      cudaStream_t st) {
+// light view of the rows selected by `mask` (NULL = all rows below the split threshold) plus, when cr.n_chunks is set,
+// one pseudo-row per chunk of the split rows; cap_view = N + chunk-row capacity; scan_in: cap_view+1 ints of scratch
+static int light_view(const int* rowptr, const int* col, long long N, long long cap_view, int split, const unsigned char* mask,
+                      ChunkRows cr, int n_part, int* light_rowptr, int* light_deg, int* light_col, int* part, int* scan_in,
+                      void* cub_temp, size_t cub_bytes, cudaStream_t st) {
   const int TB = 256;
-  k_light_deg<<<(unsigned)((N + 1 + TB - 1) / TB), TB, 0, st>>>(rowptr, N, split, mask, light_deg, scan_in);
+  k_light_deg<<<(unsigned)((cap_view + 1 + TB - 1) / TB), TB, 0, st>>>(rowptr, N, cap_view, split, mask, cr, light_deg, scan_in);
   PNA_CUDA_TRY(cudaGetLastError());
-  PNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, (const int*)scan_in, light_rowptr, (int)(N + 1), st));
-  if (N > 0 && col != nullptr) {
-    k_light_col<<<(unsigned)((N * 8 + TB - 1) / TB), TB, 0, st>>>(rowptr, light_rowptr, light_deg, col, N, light_col);
+  PNA_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, (const int*)scan_in, light_rowptr, (int)(cap_view + 1), st));
+  if (cap_view > 0 && col != nullptr) {
+    k_light_col<<<(unsigned)((cap_view * 8 + TB - 1) / TB), TB, 0, st>>>(rowptr, light_rowptr, light_deg, col, N, cap_view, cr, light_col);
     PNA_CUDA_TRY(cudaGetLastError());
   }
-  k_partition<<<(unsigned)((n_part + 1 + TB - 1) / TB), TB, 0, st>>>(light_rowptr, N, n_part, part);
+  k_partition<<<(unsigned)((n_part + 1 + TB - 1) / TB), TB, 0, st>>>(light_rowptr, N, cr.n_chunks, n_part, part);
   PNA_CUDA_TRY(cudaGetLastError());
   return PNA_OK;
 }
@@ -173,7 +212,8 @@ extern "C" int pna_csr_light_view(const int32_t* rowptr, const int32_t* col, int
   const size_t need = scan_in_bytes + align_up(scan_bytes, 256);
   PNA_REQUIRE(workspace != nullptr && workspace_bytes >= need, PNA_ERR_WORKSPACE, "pna_csr_light_view: workspace %zu bytes < required %zu", workspace_bytes, need);
   char* ws = static_cast<char*>(workspace);
-  return light_view(rowptr, col, n_nodes, split_threshold, row_mask, n_part, light_rowptr, light_deg, light_col, part,
+  ChunkRows none = {nullptr, nullptr, nullptr, 1};
+  return light_view(rowptr, col, n_nodes, n_nodes, split_threshold, row_mask, none, n_part, light_rowptr, light_deg, light_col, part,
                     reinterpret_cast<int*>(ws), ws + scan_in_bytes, scan_bytes, static_cast<cudaStream_t>(stream));
 }
 
@@ -255,10 +295,13 @@ extern "C" int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* 
   if (csr->light_rowptr) {   // light view (optional: all four arrays or none)
     PNA_REQUIRE(csr->light_deg && csr->part && (E == 0 || csr->light_col) && csr->n_part >= 1, PNA_ERR_BAD_ARG,
                 "pna_csr_build: light view needs light_rowptr, light_deg, light_col, part and n_part >= 1");
-    rc = light_view(csr->rowptr, csr->col, N, csr->split_threshold, nullptr, csr->n_part, csr->light_rowptr, csr->light_deg,
-                    csr->light_col, csr->part, keys_in, ws + L.cub_temp, L.cub_bytes, st);
+    // the view carries one pseudo-row per chunk of the split rows (capacity cap_chunks; n_chunks of them are valid)
+    const long long cap_view = N + csr->cap_chunks;
+    ChunkRows cr = {csr->hub_info, csr->chunk_items, &ctr->n_chunks, csr->chunk_edges};
+    rc = light_view(csr->rowptr, csr->col, N, cap_view, csr->split_threshold, nullptr, cr, csr->n_part, csr->light_rowptr,
+                    csr->light_deg, csr->light_col, csr->part, keys_in, ws + L.cub_temp, L.cub_bytes, st);
     if (rc != PNA_OK) return rc;
-    PNA_CUDA_TRY(cudaMemcpyAsync(&n_light, csr->light_rowptr + N, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PNA_CUDA_TRY(cudaMemcpyAsync(&n_light, csr->light_rowptr + cap_view, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   Counters host;
   PNA_CUDA_TRY(cudaMemcpyAsync(&host, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));

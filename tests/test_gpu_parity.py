@@ -89,17 +89,46 @@ def test_csr_is_stable_sort_by_destination(P, n, e, hub):
     assert torch.equal(info[:, 3], deg[info[:, 0]])
     assert torch.equal(info[:, 2], (deg[info[:, 0]] + csr.chunk_edges - 1) // csr.chunk_edges)
     assert csr.n_chunks == int(info[:, 2].sum())
-    # light view: split rows removed, slots compacted, equal-cost row partition
+    # light view: split rows removed, one pseudo-row per chunk of the split rows appended, slots compacted
     ldeg = torch.where(deg >= csr.split_threshold, torch.full_like(deg, -1), deg)
-    assert torch.equal(csr.light_deg.cpu().long(), ldeg)
-    lrp = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(ldeg.clamp(min=0), 0)])
-    assert torch.equal(csr.light_rowptr.cpu().long(), lrp)
-    assert csr.n_light_edges == int(lrp[-1])
-    keep = (ldeg >= 0)[ei[1][order]] if e else torch.zeros(0, dtype=torch.bool)
-    assert torch.equal(csr.light_col.cpu().long()[:csr.n_light_edges], ei[0][order][keep])
+    nv = n + csr.n_chunks
+    info0, items0 = csr.hub_info.cpu().long(), csr.chunk_items.cpu().long()
+    chunk_len, chunk_first = [], []
+    for c in range(csr.n_chunks):
+        h, j = int(items0[c, 0]), int(items0[c, 1])
+        chunk_len.append(min(csr.chunk_edges, int(info0[h, 3]) - j * csr.chunk_edges))
+        chunk_first.append(int(rowptr[info0[h, 0]]) + j * csr.chunk_edges)
+    # view order: one chunk row after every N // M real rows (common.cuh ViewMap)
+    M = csr.n_chunks
+    order_v = []
+    if M:
+        sreal = n // M
+        for b in range(M):
+            order_v += list(range(b * sreal, (b + 1) * sreal)) + [n + b]
+        order_v += list(range(sreal * M, n))
+    else:
+        order_v = list(range(n))
+    assert sorted(order_v) == list(range(nv))
+    row_deg = torch.cat([ldeg, torch.tensor(chunk_len, dtype=torch.long)])
+    vdeg = row_deg[torch.tensor(order_v, dtype=torch.long)] if nv else row_deg
+    assert torch.equal(csr.light_deg.cpu().long()[:nv], vdeg)
+    assert bool((csr.light_deg.cpu()[nv:] == -1).all())
+    lrp = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(vdeg.clamp(min=0), 0)])
+    assert torch.equal(csr.light_rowptr.cpu().long()[:nv + 1], lrp)
+    assert csr.n_light_edges == int(lrp[-1]) == ei.size(1)          # every slot is in the view exactly once
+    scol = ei[0][order] if e else torch.zeros(0, dtype=torch.long)
+    want_col = []
+    for r in order_v:
+        if r < n:
+            if ldeg[r] >= 0:
+                want_col.append(scol[int(rowptr[r]):int(rowptr[r + 1])])
+        else:
+            want_col.append(scol[chunk_first[r - n]:chunk_first[r - n] + chunk_len[r - n]])
+    want_col = torch.cat(want_col) if want_col else torch.zeros(0, dtype=torch.long)
+    assert torch.equal(csr.light_col.cpu().long()[:csr.n_light_edges], want_col)
     part = csr.part.cpu().long()
-    assert part[0] == 0 and part[-1] == n and bool((part[1:] >= part[:-1]).all()) and part.numel() == csr.n_part + 1
-    cost = lrp + 12 * torch.arange(n + 1)
+    assert part[0] == 0 and part[-1] == nv and bool((part[1:] >= part[:-1]).all()) and part.numel() == csr.n_part + 1
+    cost = lrp + 12 * torch.arange(nv + 1)
     width = (cost[part[1:]] - cost[part[:-1]]).float()
     if csr.n_part > 4 and n > 64:
         assert float(width.max()) <= float(cost[-1]) / csr.n_part + csr.split_threshold + 12    # balanced up to one row
