@@ -103,21 +103,36 @@ def make_workload(world: int, rank: int):
 
 
 def cpu_reference_layer(ei, x, deg_hist, steps: int, warmup: int):
-    """The reference's CPU path for PNAConvSimple.forward (port: oracle/pna_oracle.py), all host threads."""
+    """The reference's CPU path for PNAConvSimple.forward (port: oracle/pna_oracle.py) on the host cores of this box.
+
+    torch's CPU scatter/index kernels do not scale to 100+ threads (oversubscription makes them slower), so a few
+    thread counts are tried in the warm-up and the FASTEST one is timed and reported -- the baseline gets every
+    advantage the hardware offers."""
     from oracle import pna_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
     f = x.size(1)
     torch.manual_seed(0)
     lay = O.PNAConvSimpleOracle(f, f, AGGRS, SCALERS, deg_hist)
-    times = []
+    ncpu = os.cpu_count() or 1
+    candidates = sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True)
+    best_t, best_n = None, ncpu
     with torch.no_grad():
-        for i in range(warmup + steps):
+        for n in candidates:
+            torch.set_num_threads(n)
+            lay(x, ei)                                  # warm this setting
             t0 = time.perf_counter()
             lay(x, ei)
             dt = time.perf_counter() - t0
-            if i >= warmup:
+            if best_t is None or dt < best_t:
+                best_t, best_n = dt, n
+        torch.set_num_threads(best_n)
+        times = []
+        for i in range(max(0, warmup - 1) + steps):
+            t0 = time.perf_counter()
+            lay(x, ei)
+            dt = time.perf_counter() - t0
+            if i >= max(0, warmup - 1):
                 times.append(dt)
-    return times, torch.get_num_threads()
+    return times, best_n, {"threads_tried": candidates, "host_cpus": ncpu}
 
 
 def run_reference(args):
@@ -129,7 +144,7 @@ def run_reference(args):
     ei, x = make_workload(1, 0)
     n, e = x.size(0), ei.size(1)
     deg = synth.degree_histogram(ei[1], n)
-    times, threads = cpu_reference_layer(ei, x, deg, args.steps, max(1, min(args.warmup, 2)))
+    times, threads, info = cpu_reference_layer(ei, x, deg, args.steps, max(1, min(args.warmup, 2)))
     total = sum(times)
     v = e * len(times) / total
     line = {
@@ -138,7 +153,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "ogbn-arxiv-shaped CSR (configs[1])", "n_nodes": n, "n_edges": e, "n_feat": x.size(1),
                    "layer": "PNAConvSimple(128,128) forward: aggregate + post-MLP"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", **info,
                          "sample": f"full config-2 graph, {len(times)} forward passes of the reference op sequence "
                                    "(index_select, 6x scatter_add, amin, amax, degree, 3 scalers, cats, Linear) in torch CPU"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -211,9 +226,7 @@ def run_ours(args):
     clocks = clk.summary()
     t_ms = sum(per_step) / len(per_step)
     value = e / (t_ms * 1e-3)
-    light_ms = statistics.median(timed(min(args.steps, 20), 2, skip_hubs=True))
-    hubs_ms = statistics.median(timed(min(args.steps, 20), 2, skip_light=True)) if csr.n_hubs else 0.0
-    launches_per_step = 1 + (2 if csr.n_hubs else 0)
+    launches_per_step = 1 + (1 if csr.n_hubs else 0)       # k_rows_stream (+ k_hub_finalize when rows were split)
 
     bytes_ = synth.algorithmic_bytes(n, e, f, 4, 12 * f)
     peak, peak_src = measured_peaks()
@@ -266,8 +279,8 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        times, threads = cpu_reference_layer(ei, x, deg_hist, 3, 1)
-        cpu = {"value": e * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": "port",
+        times, threads, info = cpu_reference_layer(ei, x, deg_hist, 3, 1)
+        cpu = {"value": e * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": "port", **info,
                "sample": "full config-2 graph, 3 forward passes of PNAConvSimple's reference op sequence in torch CPU "
                          "(oracle/pna_oracle.py; torch_geometric/torch_scatter not installable)"}
 
@@ -282,8 +295,8 @@ def run_ours(args):
                      "traffic": traffic, "peak_source": peak_src, "bytes_model": "B_min = N*F*s + 4E + 4(N+1) + 12*N*F*s",
                      "b_min_bytes": bytes_["b_min"], "b_gather_bytes": bytes_["b_gather"],
                      "effective_gbs_b_gather": bytes_["b_gather"] / (t_ms * 1e-3) / 1e9},
-        "kernels_ms": {"k_rows": light_ms, "k_hub_chunks+k_hub_finalize": hubs_ms, "step_min": min(per_step),
-                       "step_median": statistics.median(per_step)},
+        "kernels_ms": {"step_min": min(per_step), "step_median": statistics.median(per_step),
+                       "kernels": "k_rows_stream (rows + chunks of split rows) + k_hub_finalize; per-kernel times: profiles/"},
         "layer_fwd": {"ms": full_ms, "edges_per_s": e / (full_ms * 1e-3), "what": "PNAConvSimple.forward, CSR cached, post-MLP via cuBLAS"},
         "csr_build_ms": {"first_call": csr_ms_first, "steady": csr_ms},
         "e2e": {"value": e / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,

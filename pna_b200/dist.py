@@ -288,6 +288,36 @@ def bench_multi_gpu(args, metric, unit, aggrs, scalers, measured_peaks, ClockSam
     with ClockSampler(local) as clk:
         per_step = timed(args.steps, args.warmup)
         time.sleep(0.15)
+    # e2e at N GPUs: the layer call with this rank's features in pinned host memory -- H2D of x into the symmetric /
+    # halo buffer, the fused gather+exchange aggregation, post-MLP, D2H of the rank's output rows; graph plan cached
+    from .pyg import PNAConvSimple
+    torch.manual_seed(0)
+    lay = PNAConvSimple(f, f, aggrs, scalers, deg_hist).to(dev)
+    xh = x.pin_memory()
+    outh = torch.empty((n_local, f), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        agg.x_local.copy_(xh, non_blocking=True)
+        if mode == "peer":
+            agg.barrier()
+        a = agg.aggregate(aggrs, scalers, avg_deg, out=out)
+        with torch.no_grad():
+            outh.copy_(lay.post_nn(a), non_blocking=True)
+
+    k2 = max(3, min(args.steps, 20))
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize(); dist.barrier(device_ids=[local]); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(k2):
+        e2e_step()
+    torch.cuda.synchronize(); dist.barrier(device_ids=[local])
+    e2e_ms = torch.tensor([1e3 * (time.perf_counter() - t0) / k2], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e = {"value": e_local * world / (float(e2e_ms) * 1e-3), "unit": unit, "ms_per_step": float(e2e_ms),
+           "h2d_bytes_per_step": n_local * f * 4 * world, "d2h_bytes_per_step": n_local * f * 4 * world,
+           "what": "per rank: H2D x (pinned) -> aggregation with remote sources -> post-MLP -> D2H; graph plan cached"}
+
     total_ms = torch.tensor([sum(per_step)], dtype=torch.float64, device=dev)
     dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     t_ms = float(total_ms) / args.steps
@@ -314,7 +344,7 @@ def bench_multi_gpu(args, metric, unit, aggrs, scalers, measured_peaks, ClockSam
                        "parallelism": f"dst-partition x{world}", "l2": "flushed between timed steps (512 MiB memset)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "note": "per-GPU B_min / max-over-ranks step time"},
-            "e2e": None, "gpu_launches": n_launch * args.steps, "clocks": clk.summary(), "cpu_baseline": None,
+            "e2e": e2e, "gpu_launches": n_launch * args.steps, "clocks": clk.summary(), "cpu_baseline": None,
         }
         print(json.dumps(line))
     dist.barrier(device_ids=[local])
