@@ -268,10 +268,13 @@ __device__ __forceinline__ typename Io<T, VEC>::Raw lds_raw(unsigned addr) {
 #ifndef PNA_STREAM_HALF_BYTES
 #define PNA_STREAM_HALF_BYTES 4096   // bytes of neighbour rows per ring half per warp
 #endif
-template <typename T, int VEC, int K>
+// DEPTH scales the ring: 1 for local HBM gathers; 2 when remote rows arrive over NVLink (2-3x the latency, and a row
+// at the head of the in-order ring blocks the rows behind it)
+template <typename T, int VEC, int K, int DEPTH = 1>
 struct StreamGeom {
   static constexpr int kBlockBytes = 32 * VEC * K * (int)sizeof(T);            // bytes of one ring slot
-  static constexpr int kH = (PNA_STREAM_HALF_BYTES / kBlockBytes) < 4 ? 4 : ((PNA_STREAM_HALF_BYTES / kBlockBytes) > 32 ? 32 : (PNA_STREAM_HALF_BYTES / kBlockBytes));
+  static constexpr int kHalf = PNA_STREAM_HALF_BYTES * DEPTH;
+  static constexpr int kH = (kHalf / kBlockBytes) < 4 ? 4 : ((kHalf / kBlockBytes) > 32 ? 32 : (kHalf / kBlockBytes));
   static constexpr int kWarpBytes = 2 * kH * kBlockBytes;                        // two halves
   static constexpr size_t kSmem = 128 + (size_t)(kStreamThreads / 32) * kWarpBytes;
 };
@@ -294,11 +297,11 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
 #define PNA_STREAM_TMA 0   // 1: per-row cp.async.bulk (UBLKCP) + mbarrier; 0: per-lane 16-byte cp.async (LDGSTS) groups
 #endif
 
-template <typename T, int VEC, int K, typename Cfg, bool BIAS>
+template <typename T, int VEC, int K, typename Cfg, bool BIAS, int DEPTH>
 __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_rows_stream(const KParams p) {
   constexpr int G = 32;
-  constexpr int H = StreamGeom<T, VEC, K>::kH;
-  constexpr int SLOT = StreamGeom<T, VEC, K>::kBlockBytes;
+  constexpr int H = StreamGeom<T, VEC, K, DEPTH>::kH;
+  constexpr int SLOT = StreamGeom<T, VEC, K, DEPTH>::kBlockBytes;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31;
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   // shared memory: [warps][2] mbarriers, then per warp a ring of 2*H slots
   const unsigned smem0 = smem_u32(smem);
   const unsigned bar0 = smem0 + warp * 16;
-  const unsigned ring = smem0 + 128 + warp * StreamGeom<T, VEC, K>::kWarpBytes;
+  const unsigned ring = smem0 + 128 + warp * StreamGeom<T, VEC, K, DEPTH>::kWarpBytes;
 #if PNA_STREAM_TMA
   if (lane == 0) {
     mbar_init(bar0, 1);
@@ -635,12 +638,13 @@ static int launch_config(const KParams& p, cudaStream_t st) {
       const int cfg = (s3 && (p.acodes & 0xffffu) == CfgMeanMaxMinStd::ACODES) ? 1 : 0;
       if (G == 32 && VEC > 1 && p.lrowptr != nullptr && p.col != nullptr) {
        if constexpr (G == 32 && VEC > 1) {
-        // TMA-streamed gather over the light view, persistent warps
-        constexpr size_t smem = StreamGeom<T, VEC, K>::kSmem;
+        // streamed gather over the light view, persistent warps
         const bool b = p.bias != nullptr;
-#define PNA_LAUNCH_STREAM(CFG, B)                                                                                  \
+        const bool deep = p.peer_x != nullptr;
+#define PNA_LAUNCH_STREAM(CFG, B, DEPTH)                                                                           \
   do {                                                                                                             \
-    auto kern = k_rows_stream<T, VEC, K, CFG, B>;                                                                  \
+    constexpr size_t smem = StreamGeom<T, VEC, K, DEPTH>::kSmem;                                                   \
+    auto kern = k_rows_stream<T, VEC, K, CFG, B, DEPTH>;                                                           \
     static int resident = 0;  /* CTAs of this kernel that fit the device (all B200s alike) */                     \
     if (resident == 0) {                                                                                           \
       if (smem > 48 * 1024) PNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -655,10 +659,14 @@ static int launch_config(const KParams& p, cudaStream_t st) {
     if (gxs < 1) gxs = 1;                                                                                          \
     kern<<<dim3((unsigned)gxs, gy), kStreamThreads, smem, st>>>(p);                                                \
   } while (0)
-        if (cfg == 1 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, false);
-        else if (cfg == 1) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, true);
-        else if (!b) PNA_LAUNCH_STREAM(CfgDynamic, false);
-        else PNA_LAUNCH_STREAM(CfgDynamic, true);
+        if (deep) {
+          if (cfg == 1 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, false, 2);
+          else if (!b) PNA_LAUNCH_STREAM(CfgDynamic, false, 2);
+          else PNA_LAUNCH_STREAM(CfgDynamic, true, 2);
+        } else if (cfg == 1 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, false, 1);
+        else if (cfg == 1) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, true, 1);
+        else if (!b) PNA_LAUNCH_STREAM(CfgDynamic, false, 1);
+        else PNA_LAUNCH_STREAM(CfgDynamic, true, 1);
         chunks_in_stream = p.n_view_rows > p.n_rows;
 #undef PNA_LAUNCH_STREAM
        }
