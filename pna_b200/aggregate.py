@@ -151,70 +151,35 @@ def _scaler_values(deg: torch.Tensor, scalers: list, avg_deg: Mapping[str, float
     return torch.stack(cols, 1)
 
 
-def _backward_torch(gathered, csr: CSRGraph, row_bias, messages_in_csr_order, aggregators, scalers, avg_deg, towers,
-                    has_self, grad_out, need_bias_grad):
-    """Gradient of the aggregation w.r.t. the gathered rows / row_bias with device-side torch ops.
-
-    d mean = g/cnt; d sum = g; d var = g*2(m-mean)/cnt; d std = g*[var>0](m-mean)/(cnt*std) (autograd of
-    aggregators.py:25-32); min/max route to the first slot attaining the extremum (torch_scatter arg semantics).
-    """
-    N, E = csr.n_nodes, csr.n_edges
-    F = gathered.size(1)
-    Ft = F // towers
-    A, S = len(aggregators), len(scalers)
-    dst = csr.dst_of_slot
-    col = None if messages_in_csr_order else csr.col.long()
-    go = grad_out.to(torch.float32).reshape(N, towers, (1 if has_self else 0) + S * A, Ft)
-    grad_self = go[:, :, 0, :] if has_self else None
-    go = go[:, :, (1 if has_self else 0):, :].reshape(N, towers, S, A, Ft)
-    scale = _scaler_values(csr.in_degree, scalers, avg_deg)                       # [N, S]
-    gA = (go * scale[:, None, :, None, None]).sum(2)                              # [N, T, A, Ft]
-    gA = gA.permute(0, 2, 1, 3).reshape(N, A, F)
-    m = gathered.to(torch.float32)
-    m = m if col is None else m.index_select(0, col)
+def aggregate_backward(grad_out: torch.Tensor, gathered: torch.Tensor, csr: CSRGraph, aggregators: Names, scalers: Names,
+                       avg_deg: Mapping[str, float], *, towers: int = 1, row_bias: Optional[torch.Tensor] = None,
+                       has_self: bool = False, messages_in_csr_order: bool = False, need_bias_grad: bool = False):
+    """Gradient of the aggregation w.r.t. ``gathered`` (and ``row_bias``) through ``pna_aggregate_bwd`` (fp32 results)."""
+    dev = gathered.device
+    gathered = _rows2d(gathered, "gathered")
+    F = int(gathered.size(1))
+    N = csr.n_nodes
+    n_aggr, aggr_codes = _lib.pack_codes(aggregators, _lib.AGGR_CODES, "aggregator")
+    n_scal, scal_codes = _lib.pack_codes(scalers, _lib.SCALER_CODES, "scaler")
+    grad_out = _rows2d(grad_out.to(gathered.dtype), "grad_out")
     if row_bias is not None:
-        m = m + row_bias.to(torch.float32).index_select(0, dst)
-    cnt = csr.in_degree.clamp(min=1).to(torch.float32).unsqueeze(1)
-    ssum = torch.zeros((N, F), dtype=torch.float32, device=m.device).index_add_(0, dst, m)
-    mean = ssum / cnt
-    grad_m = torch.zeros_like(m)
-    need_var = any(a in ("var", "std") for a in aggregators)
-    if need_var:
-        msq = torch.zeros((N, F), dtype=torch.float32, device=m.device).index_add_(0, dst, m * m) / cnt
-        var = msq - mean * mean
-        centred = m - mean.index_select(0, dst)
-    slot = torch.arange(E, device=m.device).unsqueeze(1)
-    for a, name in enumerate(aggregators):
-        g = gA[:, a]
-        if name == "sum":
-            grad_m += g.index_select(0, dst)
-        elif name == "mean":
-            grad_m += (g / cnt).index_select(0, dst)
-        elif name == "var":
-            grad_m += (2.0 * g / cnt).index_select(0, dst) * centred
-        elif name == "std":
-            sd = torch.sqrt(torch.relu(var) + 1e-5)
-            coef = g * (var > 0).to(torch.float32) / (sd * cnt)
-            grad_m += coef.index_select(0, dst) * centred
-        elif name in ("min", "max"):
-            red = "amin" if name == "min" else "amax"
-            ext = torch.zeros((N, F), dtype=torch.float32, device=m.device).scatter_reduce_(
-                0, dst.unsqueeze(1).expand(E, F), m, red, include_self=False)
-            hit = m == ext.index_select(0, dst)
-            cand = torch.where(hit, slot.expand(E, F), torch.full((1, 1), E, device=m.device, dtype=slot.dtype))
-            first = torch.full((N, F), E, dtype=cand.dtype, device=m.device).scatter_reduce_(
-                0, dst.unsqueeze(1).expand(E, F), cand, "amin", include_self=True)
-            grad_m += g.index_select(0, dst) * (cand == first.index_select(0, dst)).to(torch.float32)
-        else:
-            raise KeyError(name)
-    if col is None:
-        grad_g = grad_m
-    else:
-        grad_g = torch.zeros((gathered.size(0), F), dtype=torch.float32, device=m.device).index_add_(0, col, grad_m)
-    grad_b = None
-    if need_bias_grad:
-        grad_b = torch.zeros((N, F), dtype=torch.float32, device=m.device).index_add_(0, dst, grad_m)
-    return grad_g, grad_b, grad_self
+        row_bias = _rows2d(row_bias.to(gathered.dtype), "row_bias")
+    gg = torch.zeros((gathered.size(0), F), dtype=torch.float32, device=dev)
+    gb = torch.empty((N, F), dtype=torch.float32, device=dev) if need_bias_grad else None
+    d = _lib.AggStruct(
+        gathered=_ptr(gathered), ld_gathered=gathered.stride(0) if gathered.size(0) > 1 else F,
+        rowptr=_ptr(csr.rowptr), col=None if messages_in_csr_order else (_ptr(csr.col) if csr.n_edges else None),
+        row_bias=_ptr(row_bias), ld_row_bias=0 if row_bias is None else (row_bias.stride(0) if N > 1 else F),
+        self_feat=1 if has_self else None,     # only its presence matters here: it shifts the grad_out columns
+        n_rows=N, n_feat=F, n_towers=towers, dtype=_DTYPES[gathered.dtype],
+        n_aggr=n_aggr, aggr_codes=aggr_codes, n_scalers=n_scal, scaler_codes=scal_codes,
+        avg_log=float(avg_deg["log"]), avg_lin=float(avg_deg.get("lin", 1.0)),
+        split_threshold=csr.split_threshold, chunk_edges=csr.chunk_edges,
+        hub_info=_ptr(csr.hub_info) if csr.n_hubs else None, n_hubs=csr.n_hubs, n_chunks=csr.n_chunks)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pna_aggregate_bwd(C.byref(d), grad_out.data_ptr(), grad_out.stride(0) if N > 1 else grad_out.size(1),
+                                                gg.data_ptr(), F, _ptr(gb), F, torch.cuda.current_stream(dev).cuda_stream))
+    return gg, gb
 
 
 class _PNAAggregate(torch.autograd.Function):
@@ -232,14 +197,16 @@ class _PNAAggregate(torch.autograd.Function):
     def backward(ctx, grad_out):
         gathered, row_bias, self_feat = ctx.saved_tensors
         csr, aggregators, scalers, avg_deg, towers, self_divided, in_order = ctx.meta
-        grad_g, grad_b, grad_self = _backward_torch(
-            gathered, csr, row_bias, in_order, aggregators, scalers, avg_deg, towers, self_feat is not None,
-            grad_out, ctx.needs_input_grad[1])
+        grad_g, grad_b = aggregate_backward(
+            grad_out, gathered, csr, aggregators, scalers, avg_deg, towers=towers, row_bias=row_bias,
+            has_self=self_feat is not None, messages_in_csr_order=in_order, need_bias_grad=ctx.needs_input_grad[1])
         gs = None
         if self_feat is not None and ctx.needs_input_grad[2]:
-            # [N, T, Ft] -> divided: [N, F]; repeated: sum over towers
-            gs = grad_self.reshape(csr.n_nodes, -1) if self_divided else grad_self.sum(1)
-            gs = gs.to(self_feat.dtype)
+            # the self block of every tower is a plain copy: its gradient is the matching slice of grad_out
+            N, F = csr.n_nodes, gathered.size(1)
+            Ft = F // towers
+            blk = grad_out.reshape(N, towers, -1)[:, :, :Ft]
+            gs = (blk.reshape(N, F) if self_divided else blk.sum(1)).to(self_feat.dtype)
         return (grad_g.to(gathered.dtype) if ctx.needs_input_grad[0] else None,
                 grad_b.to(row_bias.dtype) if (grad_b is not None) else None, gs,
                 None, None, None, None, None, None, None, None)

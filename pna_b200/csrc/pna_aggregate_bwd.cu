@@ -1,0 +1,354 @@
+// pna_aggregate_bwd: gradient of the aggregation w.r.t. the gathered rows (and the destination-side row_bias).
+//
+// Autograd of reference models/pytorch_geometric/aggregators.py:9-32 + scalers.py:8-29, as every training loop needs
+// (multitask_benchmark/util/train.py:148, realworld_benchmark/train/*.py:31):
+//   g_a   = sum over scalers s of scale_s(d) * grad_out[(s*A + a)*F + f]                        (per aggregator a)
+//   d sum/dm = 1;  d mean/dm = 1/cnt;  d var/dm = 2 (m - mean)/cnt;  d std/dm = [var > 0] (m - mean)/(cnt * std)
+//   min / max route to the FIRST slot attaining the extremum (torch_scatter's arg semantics)
+// so that  grad_m(slot) = c0 + c1 * m + [slot == argmin] g_min + [slot == argmax] g_max  with two per-row coefficients.
+// Two passes over the slots of a row: (A) recompute sum, sumsq, min, max and the first arg slots exactly as the forward
+// does; (C) evaluate grad_m per slot, accumulate it into grad_gathered[col[slot]] (vector atomics -- several
+// destinations share a source) and into grad_row_bias[row].  Rows at/above the split threshold get one CTA each.
+#include "pna_aggregate.cuh"
+#include <string.h>
+
+namespace pna {
+
+struct BParams {
+  KParams k;
+  const void* go; long long ldgo;     // grad_out, layout of out
+  float* gg; long long ldgg;          // grad_gathered [n_src, F] fp32, accumulated
+  float* gb; long long ldgb;          // grad_row_bias [n_rows, F] fp32, written (nullable)
+  int vec_atomics;                    // grad_gathered rows are 16-byte aligned
+};
+
+template <int VEC>
+struct Stats {
+  float sum[VEC], sq[VEC], mn[VEC], mx[VEC];
+  int amn[VEC], amx[VEC];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { sum[i] = 0.f; sq[i] = 0.f; mn[i] = CUDART_INF_F; mx[i] = -CUDART_INF_F; amn[i] = -1; amx[i] = -1; }
+  }
+  __device__ __forceinline__ void add(const float (&m)[VEC], int slot) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      sum[i] = __fadd_rn(sum[i], m[i]);
+      sq[i] = __fadd_rn(sq[i], __fmul_rn(m[i], m[i]));
+      if (m[i] < mn[i]) { mn[i] = m[i]; amn[i] = slot; }   // strict: the first slot attaining the extremum wins
+      if (m[i] > mx[i]) { mx[i] = m[i]; amx[i] = slot; }
+    }
+  }
+};
+
+template <int VEC>
+struct Coef {
+  float c0[VEC], c1[VEC], gmin[VEC], gmax[VEC];
+};
+
+template <typename T, int VEC>
+__device__ __forceinline__ void load_m(const KParams& p, int src, int f, const float (&bias)[VEC], bool has_bias, float (&m)[VEC]) {
+  Io<T, VEC>::load(gathered_row<T>(p, src) + f, m);
+  if (has_bias) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) m[i] = __fadd_rn(m[i], bias[i]);
+  }
+}
+
+// upstream gradients of one row -> the two coefficients and the min / max gradients
+template <typename T, int VEC>
+__device__ __forceinline__ void coefficients(const BParams& b, long long row, int deg, int ooff, const Stats<VEC>& st, Coef<VEC>& c) {
+  const KParams& p = b.k;
+  const bool iso = deg == 0;
+  const float degf = (float)deg, cnt = iso ? 1.0f : degf;
+  const float lg = logf(degf + 1.0f);
+  const float s_amp = lg / p.avg_log, s_att = iso ? 1.0f : p.avg_log / lg;
+  const float s_lin = degf / p.avg_lin, s_ilin = iso ? 1.0f : p.avg_lin / degf;
+  const T* __restrict__ gorow = static_cast<const T*>(b.go) + row * b.ldgo + ooff;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { c.c0[i] = 0.f; c.c1[i] = 0.f; c.gmin[i] = 0.f; c.gmax[i] = 0.f; }
+  float mean[VEC], var[VEC], sd[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    mean[i] = st.sum[i] / cnt;
+    var[i] = st.sq[i] / cnt - mean[i] * mean[i];
+    sd[i] = sqrtf(fmaxf(var[i], 0.f) + 1e-5f);
+  }
+  for (int a = 0; a < p.nA; ++a) {
+    const unsigned ac = (p.acodes >> (4 * a)) & 15u;
+    if (ac == PNA_AGGR_SKIP) continue;
+    float g[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) g[i] = 0.f;
+    for (int s = 0; s < p.nS; ++s) {
+      const unsigned sc = (p.scodes >> (4 * s)) & 15u;
+      const float scale = sc == PNA_SCALE_IDENTITY ? 1.0f : sc == PNA_SCALE_AMPLIFICATION ? s_amp : sc == PNA_SCALE_ATTENUATION ? s_att
+                          : sc == PNA_SCALE_LINEAR ? s_lin : s_ilin;
+      float go[VEC];
+      Io<T, VEC>::load(gorow + (s * p.nA + a) * p.Ft, go);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) g[i] += scale * go[i];
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      switch (ac) {
+        case PNA_AGGR_SUM: c.c0[i] += g[i]; break;
+        case PNA_AGGR_MEAN: c.c0[i] += g[i] / cnt; break;
+        case PNA_AGGR_MIN: c.gmin[i] += g[i]; break;
+        case PNA_AGGR_MAX: c.gmax[i] += g[i]; break;
+        case PNA_AGGR_VAR: { const float t = 2.0f * g[i] / cnt; c.c1[i] += t; c.c0[i] -= t * mean[i]; } break;
+        default: { const float t = var[i] > 0.f ? g[i] / (cnt * sd[i]) : 0.f; c.c1[i] += t; c.c0[i] -= t * mean[i]; } break;
+      }
+    }
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void scatter_grad(const BParams& b, long long src_row, int f, const float (&gm)[VEC], bool atomic) {
+  float* dst = b.gg + src_row * b.ldgg + f;
+  if (!atomic) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) dst[i] = gm[i];
+    return;
+  }
+  if constexpr (VEC % 4 == 0) {
+    if (b.vec_atomics) {
+#pragma unroll
+      for (int i = 0; i < VEC; i += 4) atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(gm[i], gm[i + 1], gm[i + 2], gm[i + 3]));
+      return;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) atomicAdd(dst + i, gm[i]);
+}
+
+// feature column / output column of this lane
+struct LaneCols { int f, ooff; bool ok; };
+template <int VEC>
+__device__ __forceinline__ LaneCols lane_cols(const KParams& p, int gl, int fblock) {
+  LaneCols c;
+  c.f = fblock + gl * VEC;
+  c.ok = c.f < p.F;
+  if (!c.ok) { c.f = 0; }
+  const int t = c.f / p.Ft, ft = c.f - t * p.Ft;
+  c.ooff = t * p.Wt + p.has_self * p.Ft + ft;
+  return c;
+}
+
+constexpr int kBwdThreads = 256;
+
+// ---- rows below the split threshold: one lane group per row --------------------------------------------------------
+template <typename T, int VEC, int G>
+__global__ void __launch_bounds__(kBwdThreads) k_bwd_rows(const BParams b) {
+  const KParams& p = b.k;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane % G;
+  const long long row = ((long long)blockIdx.x * (kBwdThreads / 32) + (threadIdx.x >> 5)) * RPW + lane / G;
+  if (row >= p.n_rows) return;
+  const LaneCols lc = lane_cols<VEC>(p, gl, blockIdx.y * (G * VEC));
+  if (!lc.ok) return;
+  const int beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1), deg = end - beg;
+  if (deg >= p.split) return;
+  const bool has_bias = p.bias != nullptr;
+  float bias[VEC];
+  if (has_bias) Io<T, VEC>::load(static_cast<const T*>(p.bias) + row * p.ldb + lc.f, bias);
+  if (deg == 0) {
+    if (b.gb) {
+      float z[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) z[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) b.gb[row * b.ldgb + lc.f + i] = z[i];
+    }
+    return;
+  }
+  Stats<VEC> st;
+  st.init();
+  for (int e = beg; e < end; ++e) {
+    float m[VEC];
+    load_m<T, VEC>(p, p.col ? __ldg(p.col + e) : e, lc.f, bias, has_bias, m);
+    st.add(m, e);
+  }
+  Coef<VEC> c;
+  coefficients<T, VEC>(b, row, deg, lc.ooff, st, c);
+  float gbs[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) gbs[i] = 0.f;
+  for (int e = beg; e < end; ++e) {
+    const int src = p.col ? __ldg(p.col + e) : e;
+    float m[VEC], gm[VEC];
+    load_m<T, VEC>(p, src, lc.f, bias, has_bias, m);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      gm[i] = c.c0[i] + c.c1[i] * m[i] + (e == st.amn[i] ? c.gmin[i] : 0.f) + (e == st.amx[i] ? c.gmax[i] : 0.f);
+      gbs[i] += gm[i];
+    }
+    scatter_grad<VEC>(b, src, lc.f, gm, p.col != nullptr);
+  }
+  if (b.gb) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) b.gb[row * b.ldgb + lc.f + i] = gbs[i];
+  }
+}
+
+// ---- split rows: one CTA per row, NG lane groups over contiguous slot ranges, statistics merged in shared memory ----
+constexpr int kBwdGroups = 8;
+
+template <typename T, int VEC, int G>
+__global__ void __launch_bounds__(kBwdGroups * 32) k_bwd_hubs(const BParams b) {
+  const KParams& p = b.k;
+  extern __shared__ float sm[];
+  constexpr int W = G * VEC;                   // columns of this feature block
+  float* s_sum = sm;                           // [NG][W] each
+  float* s_sq = s_sum + kBwdGroups * W;
+  float* s_mn = s_sq + kBwdGroups * W;
+  float* s_mx = s_mn + kBwdGroups * W;
+  int* s_amn = reinterpret_cast<int*>(s_mx + kBwdGroups * W);
+  int* s_amx = s_amn + kBwdGroups * W;
+  const int gl = threadIdx.x % G, q = threadIdx.x / G;
+  const long long h = blockIdx.x;
+  const long long row = __ldg(p.hub_info + 4 * h);
+  const int deg = __ldg(p.hub_info + 4 * h + 3);
+  const int beg = __ldg(p.rowptr + row);
+  const LaneCols lc = lane_cols<VEC>(p, gl, blockIdx.y * W);
+  const bool has_bias = p.bias != nullptr;
+  float bias[VEC];
+  if (has_bias && lc.ok) Io<T, VEC>::load(static_cast<const T*>(p.bias) + row * p.ldb + lc.f, bias);
+  const int per = (deg + kBwdGroups - 1) / kBwdGroups;
+  const int e0 = beg + q * per, e1 = min(beg + deg, e0 + per);
+  Stats<VEC> st;
+  st.init();
+  if (lc.ok) {
+    for (int e = e0; e < e1; ++e) {
+      float m[VEC];
+      load_m<T, VEC>(p, p.col ? __ldg(p.col + e) : e, lc.f, bias, has_bias, m);
+      st.add(m, e);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int o = q * W + gl * VEC + i;
+      s_sum[o] = st.sum[i]; s_sq[o] = st.sq[i]; s_mn[o] = st.mn[i]; s_mx[o] = st.mx[i]; s_amn[o] = st.amn[i]; s_amx[o] = st.amx[i];
+    }
+  }
+  __syncthreads();
+  Coef<VEC> c;
+  if (lc.ok) {
+    st.init();
+    for (int g = 0; g < kBwdGroups; ++g) {      // groups hold increasing slot ranges: strict < keeps the first attaining slot
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int o = g * W + gl * VEC + i;
+        st.sum[i] += s_sum[o]; st.sq[i] += s_sq[o];
+        if (s_mn[o] < st.mn[i]) { st.mn[i] = s_mn[o]; st.amn[i] = s_amn[o]; }
+        if (s_mx[o] > st.mx[i]) { st.mx[i] = s_mx[o]; st.amx[i] = s_amx[o]; }
+      }
+    }
+    coefficients<T, VEC>(b, row, deg, lc.ooff, st, c);
+  }
+  __syncthreads();   // s_sum is reused for the row_bias gradient below
+  float gbs[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) gbs[i] = 0.f;
+  if (lc.ok) {
+    for (int e = e0; e < e1; ++e) {
+      const int src = p.col ? __ldg(p.col + e) : e;
+      float m[VEC], gm[VEC];
+      load_m<T, VEC>(p, src, lc.f, bias, has_bias, m);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        gm[i] = c.c0[i] + c.c1[i] * m[i] + (e == st.amn[i] ? c.gmin[i] : 0.f) + (e == st.amx[i] ? c.gmax[i] : 0.f);
+        gbs[i] += gm[i];
+      }
+      scatter_grad<VEC>(b, src, lc.f, gm, p.col != nullptr);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s_sum[q * W + gl * VEC + i] = gbs[i];
+  }
+  __syncthreads();
+  if (b.gb && lc.ok && q == 0) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float t = 0.f;
+      for (int g = 0; g < kBwdGroups; ++g) t += s_sum[g * W + gl * VEC + i];
+      b.gb[row * b.ldgb + lc.f + i] = t;
+    }
+  }
+}
+
+template <typename T, int VEC, int G>
+static int launch_bwd(const BParams& b, cudaStream_t st) {
+  const KParams& p = b.k;
+  constexpr int RPW = 32 / G;
+  const unsigned gy = (unsigned)((p.F + G * VEC - 1) / (G * VEC));
+  const long long per_block = (kBwdThreads / 32) * RPW;
+  const long long gx = (p.n_rows + per_block - 1) / per_block;
+  PNA_REQUIRE(gx <= 0x7fffffffll, PNA_ERR_UNSUPPORTED, "pna_aggregate_bwd: too many rows");
+  k_bwd_rows<T, VEC, G><<<dim3((unsigned)gx, gy), kBwdThreads, 0, st>>>(b);
+  PNA_CUDA_TRY(cudaGetLastError());
+  if (p.n_hubs > 0) {
+    const size_t smem = (size_t)kBwdGroups * G * VEC * 6 * sizeof(float);
+    k_bwd_hubs<T, VEC, G><<<dim3((unsigned)p.n_hubs, gy), kBwdGroups * G, smem, st>>>(b);
+    PNA_CUDA_TRY(cudaGetLastError());
+  }
+  return PNA_OK;
+}
+
+template <typename T, int VEC>
+static int launch_bwd_typed(const BParams& b, cudaStream_t st) {
+  const int chunks = b.k.F / VEC;
+  if (chunks <= 1) return launch_bwd<T, VEC, 1>(b, st);
+  if (chunks <= 2) return launch_bwd<T, VEC, 2>(b, st);
+  if (chunks <= 4) return launch_bwd<T, VEC, 4>(b, st);
+  if (chunks <= 8) return launch_bwd<T, VEC, 8>(b, st);
+  if (chunks <= 16) return launch_bwd<T, VEC, 16>(b, st);
+  return launch_bwd<T, VEC, 32>(b, st);     // wider rows: several feature blocks (gridDim.y)
+}
+
+static bool al16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
+
+}  // namespace pna
+
+using namespace pna;
+
+extern "C" int pna_aggregate_bwd(const pna_agg_t* d, const void* grad_out, int64_t ld_grad_out, float* grad_gathered,
+                                 int64_t ld_grad_gathered, float* grad_row_bias, int64_t ld_grad_row_bias, pna_stream_t stream) {
+  PNA_REQUIRE(d != nullptr, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: null descriptor");
+  PNA_REQUIRE(d->n_rows >= 0 && d->n_feat > 0 && d->n_towers > 0 && d->n_feat % d->n_towers == 0, PNA_ERR_BAD_ARG,
+              "pna_aggregate_bwd: bad sizes");
+  PNA_REQUIRE(d->n_aggr >= 1 && d->n_aggr <= PNA_MAX_AGGR && d->n_scalers >= 1 && d->n_scalers <= PNA_MAX_SCALERS, PNA_ERR_BAD_ARG,
+              "pna_aggregate_bwd: n_aggr / n_scalers out of range");
+  PNA_REQUIRE(d->dtype == PNA_F32 || d->dtype == PNA_BF16, PNA_ERR_UNSUPPORTED, "pna_aggregate_bwd: dtype %d", d->dtype);
+  if (d->n_rows == 0) return PNA_OK;
+  PNA_REQUIRE(d->gathered && d->rowptr && grad_out && grad_gathered, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: null pointer");
+  PNA_REQUIRE(d->peer_gathered == nullptr, PNA_ERR_UNSUPPORTED, "pna_aggregate_bwd: peer-memory graphs are forward-only");
+  PNA_REQUIRE(d->split_threshold >= 2, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: bad split threshold");
+  if (d->n_hubs > 0) PNA_REQUIRE(d->hub_info != nullptr, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: hub_info missing");
+
+  BParams b;
+  memset(&b, 0, sizeof(b));
+  KParams& p = b.k;
+  p.x = d->gathered; p.ldx = d->ld_gathered;
+  p.rowptr = d->rowptr; p.col = d->col;
+  p.bias = d->row_bias; p.ldb = d->ld_row_bias;
+  p.n_rows = d->n_rows;
+  p.F = d->n_feat; p.T = d->n_towers; p.Ft = d->n_feat / d->n_towers;
+  p.has_self = d->self_feat ? 1 : 0;
+  p.nA = d->n_aggr; p.nS = d->n_scalers; p.acodes = d->aggr_codes; p.scodes = d->scaler_codes;
+  p.Wt = (p.has_self + p.nA * p.nS) * p.Ft;
+  p.avg_log = d->avg_log; p.avg_lin = d->avg_lin;
+  p.flags = d->flags; p.split = d->split_threshold; p.chunk = d->chunk_edges;
+  p.hub_info = d->hub_info; p.n_hubs = d->n_hubs;
+  b.go = grad_out; b.ldgo = ld_grad_out;
+  b.gg = grad_gathered; b.ldgg = ld_grad_gathered;
+  b.gb = grad_row_bias; b.ldgb = ld_grad_row_bias;
+  PNA_REQUIRE(b.ldgo >= (long long)p.T * p.Wt, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: ld_grad_out too small");
+  b.vec_atomics = al16(grad_gathered) && (ld_grad_gathered % 4 == 0);
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int esz = d->dtype == PNA_F32 ? 4 : 2;
+  const int vec = 16 / esz;
+  bool vec_ok = (p.Ft % vec == 0) && al16(p.x) && al16(grad_out) && (p.ldx % vec == 0) && (b.ldgo % vec == 0);
+  if (p.bias) vec_ok = vec_ok && al16(p.bias) && (p.ldb % vec == 0);
+  if (d->dtype == PNA_F32) return vec_ok ? launch_bwd_typed<float, 4>(b, st) : launch_bwd_typed<float, 1>(b, st);
+  return vec_ok ? launch_bwd_typed<__nv_bfloat16, 8>(b, st) : launch_bwd_typed<__nv_bfloat16, 1>(b, st);
+}

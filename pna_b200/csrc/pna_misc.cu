@@ -90,11 +90,3 @@ extern "C" int pna_gather_rows(const void* src, int64_t ld_src, const int32_t* i
   PNA_CUDA_TRY(cudaGetLastError());
   return PNA_OK;
 }
-
-extern "C" int pna_aggregate_bwd(const pna_agg_t* desc, const void* grad_out, int64_t ld_grad_out, float* grad_gathered,
-                                 int64_t ld_grad_gathered, float* grad_row_bias, int64_t ld_grad_row_bias, pna_stream_t stream) {
-  (void)desc; (void)grad_out; (void)ld_grad_out; (void)grad_gathered; (void)ld_grad_gathered; (void)grad_row_bias;
-  (void)ld_grad_row_bias; (void)stream;
-  set_error("pna_aggregate_bwd: not built into this library version");
-  return PNA_ERR_UNSUPPORTED;
-}
