@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import padding as pad
 from .aggregate import pna_aggregate
 from .graph import graph_csr
 from .nn_blocks import FCLayer, MLP
@@ -46,9 +47,14 @@ class PNATower(nn.Module):
         self.posttrans = MLP(in_size=(len(aggregators) * len(scalers) + 1) * in_dim, hidden_size=out_dim, out_size=out_dim,
                              layers=posttrans_layers, mid_activation="relu", last_activation="none")
 
-    def finish(self, h_cat, snorm_n):
-        """posttrans -> graph norm -> batch norm -> dropout (pna_layer.py:67-76)."""
-        h = self.posttrans(h_cat)
+    def finish(self, h_cat, snorm_n, blocks=None, fp=None):
+        """posttrans -> graph norm -> batch norm -> dropout (pna_layer.py:67-76).  h_cat may carry padded column blocks
+        (width fp instead of in_dim): the first posttrans Linear then gets zero weight columns at the pad positions."""
+        if fp is not None and fp != self.in_dim:
+            w0 = pad.expand_weight_cols(self.posttrans.fully_connected[0].linear.weight, blocks, self.in_dim, fp)
+            h = self.posttrans(h_cat, first_weight=w0)
+        else:
+            h = self.posttrans(h_cat)
         if self.graph_norm:
             h = h * snorm_n
         if self.batch_norm:
@@ -85,12 +91,14 @@ class PNALayer(nn.Module):
         it = self.input_tower
         return h[:, t * it:(t + 1) * it] if self.divide_input else h
 
-    def _affine_terms(self, h):
-        """pretrans(cat[src h, dst h]) = W_s h_src + W_d h_dst + b (pna_layer.py:35-40): V = h W_s^T + b, U = h W_d^T."""
+    def _affine_terms(self, h, fp):
+        """pretrans(cat[src h, dst h]) = W_s h_src + W_d h_dst + b (pna_layer.py:35-40): V = h W_s^T + b, U = h W_d^T,
+        each tower block padded to fp columns with zero weight rows."""
         it = self.input_tower
         lins = [tw.pretrans.fully_connected[0].linear for tw in self.towers]
-        Ws, Wd = [l.weight[:, :it] for l in lins], [l.weight[:, it:2 * it] for l in lins]
-        b = torch.cat([l.bias for l in lins])
+        Ws = [pad.expand_weight_rows(l.weight[:, :it], it, fp) for l in lins]
+        Wd = [pad.expand_weight_rows(l.weight[:, it:2 * it], it, fp) for l in lins]
+        b = torch.cat([F.pad(l.bias, (0, fp - it)) for l in lins])
         if self.divide_input and len(lins) > 1:
             V = torch.addmm(b, h, torch.block_diag(*Ws).t())
             U = h @ torch.block_diag(*Wd).t()
@@ -112,16 +120,24 @@ class PNALayer(nn.Module):
     def forward(self, g, h, e, snorm_n):
         h_in = h
         csr = graph_csr(g, h.device)
-        T = len(self.towers)
-        common = dict(towers=T, self_feat=h, self_divided=self.divide_input, zero_isolated=True)
+        T, it = len(self.towers), self.input_tower
+        fp = pad.padded_width(it, h.dtype)
+        if fp == it:
+            h_self = h
+        elif self.divide_input:
+            h_self = pad.pad_blocks(h, T, it, fp)
+        else:
+            h_self = pad.pad_cols(h, fp)
+        common = dict(towers=T, self_feat=h_self, self_divided=self.divide_input, zero_isolated=True)
         if not self.edge_features and self.towers[0].pretrans.is_single_affine():
-            U, V = self._affine_terms(h)
+            U, V = self._affine_terms(h, fp)
             agg = pna_aggregate(V, csr, self.aggregators, self.scalers, self.avg_d, row_bias=U, **common)
         else:
-            agg = pna_aggregate(self._edge_messages(csr, h, e), csr, self.aggregators, self.scalers, self.avg_d,
-                                messages_in_csr_order=True, **common)
-        agg = agg.view(h.size(0), T, -1)                                  # [N, T, (1 + S*A) * in_t] = cat([h_t, reduced])
-        h_cat = torch.cat([tw.finish(agg[:, t], snorm_n) for t, tw in enumerate(self.towers)], dim=1)
+            msgs = pad.pad_blocks(self._edge_messages(csr, h, e), T, it, fp)
+            agg = pna_aggregate(msgs, csr, self.aggregators, self.scalers, self.avg_d, messages_in_csr_order=True, **common)
+        agg = agg.view(h.size(0), T, -1)                                  # [N, T, (1 + S*A) * fp] = cat([h_t, reduced])
+        blocks = 1 + len(self.aggregators) * len(self.scalers)
+        h_cat = torch.cat([tw.finish(agg[:, t], snorm_n, blocks, fp) for t, tw in enumerate(self.towers)], dim=1)
         h_out = self.mixing_network(h_cat)
         if self.residual:
             h_out = h_in + h_out
@@ -150,7 +166,15 @@ class PNASimpleLayer(nn.Module):
 
     def forward(self, g, h):
         h_in = h
-        h = self.posttrans(self.aggregate_only(g, h))
+        fp = pad.padded_width(self.in_dim, h.dtype)
+        if fp == self.in_dim:
+            h = self.posttrans(self.aggregate_only(g, h))
+        else:   # odd width: 128-bit path on zero-padded rows, padding absorbed by the first posttrans Linear
+            agg = pna_aggregate(pad.pad_cols(h, fp), graph_csr(g, h.device), self.aggregators, self.scalers, self.avg_d,
+                                zero_isolated=True)
+            blocks = len(self.aggregators) * len(self.scalers)
+            w0 = pad.expand_weight_cols(self.posttrans.fully_connected[0].linear.weight, blocks, self.in_dim, fp)
+            h = self.posttrans(agg, first_weight=w0)
         if self.batch_norm:
             h = self.batchnorm_h(h)
         h = F.relu(h)

@@ -46,8 +46,9 @@ class FCLayer(nn.Module):
         if self.bias:
             self.linear.bias.data.zero_()
 
-    def forward(self, x):
-        h = self.linear(x)
+    def forward(self, x, weight=None):
+        """`weight`: optional replacement for linear.weight (same parameters, zero columns inserted for padded inputs)."""
+        h = self.linear(x) if weight is None else nn.functional.linear(x, weight, self.linear.bias)
         if self.activation is not None:
             h = self.activation(h)
         if self.dropout is not None:
@@ -74,9 +75,9 @@ class MLP(nn.Module):
             self.fully_connected.append(FCLayer(sizes[k], sizes[k + 1], activation=last_activation if last else mid_activation,
                                                 b_norm=last_b_norm if last else mid_b_norm, device=device, dropout=dropout))
 
-    def forward(self, x):
-        for fc in self.fully_connected:
-            x = fc(x)
+    def forward(self, x, first_weight=None):
+        for k, fc in enumerate(self.fully_connected):
+            x = fc(x, first_weight) if (k == 0 and first_weight is not None) else fc(x)
         return x
 
     def is_single_affine(self) -> bool:

@@ -13,6 +13,7 @@ import torch
 from torch import Tensor
 from torch.nn import Linear, Module, ModuleList, ReLU, Sequential
 
+from . import padding as pad
 from .aggregate import avg_deg_from_histogram, pna_aggregate
 from .csr import CSRGraph, csr_from_edge_index
 
@@ -78,8 +79,18 @@ class PNAConvSimple(Module):
                 deg: Optional[Tensor] = None, csr: Optional[CSRGraph] = None) -> Tensor:
         # `deg` (precomputed in-degree) is accepted for signature compatibility with BASELINE.json's wording; the
         # in-degree always comes from the CSR row pointer, which is what degree(index) recounts in pna.py:247.
-        out = self.aggregate_only(x, edge_index, csr)
-        return self.post_nn(out)
+        Fp = pad.padded_width(self.F_in, x.dtype)
+        if Fp == self.F_in:
+            return self.post_nn(self.aggregate_only(x, edge_index, csr))
+        # odd width (e.g. 75): run the 128-bit path on zero-padded rows, absorb the padding in the first Linear
+        csr = _resolve_csr(x, edge_index, csr)
+        out = pna_aggregate(pad.pad_cols(x, Fp), csr, self.aggregators, self.scalers, self.avg_deg)
+        blocks = len(self.aggregators) * len(self.scalers)
+        lin0 = self.post_nn[0]
+        out = torch.nn.functional.linear(out, pad.expand_weight_cols(lin0.weight, blocks, self.F_in, Fp), lin0.bias)
+        for m in list(self.post_nn)[1:]:
+            out = m(out)
+        return out
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels})"
@@ -141,14 +152,15 @@ class PNAConv(Module):
         self.lin.reset_parameters()
 
     # -- message side ---------------------------------------------------------------------------------------------
-    def _affine_terms(self, x: Tensor):
-        """U = x W_i^T (destination side), V = x W_j^T + b (source side), both [N, T*F_in]."""
+    def _affine_terms(self, x: Tensor, Fp: int):
+        """U = x W_i^T (destination side), V = x W_j^T + b (source side), both [N, T*Fp]; Fp >= F_in pads every tower
+        block with zero features (zero weight rows: the GEMM writes them)."""
         T, Fi = self.towers, self.F_in
-        Wi = [nn[0].weight[:, :Fi] for nn in self.pre_nns]
-        Wj = [nn[0].weight[:, Fi:2 * Fi] for nn in self.pre_nns]
-        b = torch.cat([nn[0].bias for nn in self.pre_nns])
+        Wi = [pad.expand_weight_rows(nn[0].weight[:, :Fi], Fi, Fp) for nn in self.pre_nns]
+        Wj = [pad.expand_weight_rows(nn[0].weight[:, Fi:2 * Fi], Fi, Fp) for nn in self.pre_nns]
+        b = torch.cat([torch.nn.functional.pad(nn[0].bias, (0, Fp - Fi)) for nn in self.pre_nns])
         if self.divide_input and T > 1:
-            # tower t only sees its own F_in input columns: block-diagonal [T*F_in, T*F_in] weight, one GEMM
+            # tower t only sees its own F_in input columns: block-diagonal [T*Fp, T*F_in] weight, one GEMM
             U = x @ torch.block_diag(*Wi).t()
             V = torch.addmm(b, x, torch.block_diag(*Wj).t())
         else:
@@ -173,17 +185,31 @@ class PNAConv(Module):
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Optional[Tensor] = None, *,
                 deg: Optional[Tensor] = None, csr: Optional[CSRGraph] = None) -> Tensor:
         csr = _resolve_csr(x, edge_index, csr)
-        T = self.towers
-        common = dict(towers=T, self_feat=x, self_divided=self.divide_input)
+        T, Fi = self.towers, self.F_in
+        Fp = pad.padded_width(Fi, x.dtype)
+        # self features at the (possibly padded) tower width
+        if Fp == Fi:
+            x_self = x
+        elif self.divide_input:
+            x_self = pad.pad_blocks(x, T, Fi, Fp)
+        else:
+            x_self = pad.pad_cols(x, Fp)
+        common = dict(towers=T, self_feat=x_self, self_divided=self.divide_input)
         if edge_attr is None and self.pre_layers == 1 and self.edge_dim is None:
-            U, V = self._affine_terms(x)
+            U, V = self._affine_terms(x, Fp)
             out = pna_aggregate(V, csr, self.aggregators, self.scalers, self.avg_deg, row_bias=U, **common)
         else:
-            msgs = self._messages_in_slot_order(x, csr, edge_attr)
+            msgs = pad.pad_blocks(self._messages_in_slot_order(x, csr, edge_attr), T, Fi, Fp)
             out = pna_aggregate(msgs, csr, self.aggregators, self.scalers, self.avg_deg, messages_in_csr_order=True,
                                 **common)
-        out = out.view(x.size(0), T, -1)                       # [N, T, (1 + S*A) * F_in]  (pna.py:131)
-        outs = [nn(out[:, t]) for t, nn in enumerate(self.post_nns)]
+        out = out.view(x.size(0), T, -1)                       # [N, T, (1 + S*A) * Fp]  (pna.py:131)
+        blocks = 1 + len(self.aggregators) * len(self.scalers)
+        outs = []
+        for t, nn in enumerate(self.post_nns):
+            h = torch.nn.functional.linear(out[:, t], pad.expand_weight_cols(nn[0].weight, blocks, Fi, Fp), nn[0].bias)
+            for m in list(nn)[1:]:
+                h = m(h)
+            outs.append(h)
         out = torch.cat(outs, dim=1) if T > 1 else outs[0]
         return self.lin(out)
 

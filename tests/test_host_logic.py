@@ -56,7 +56,7 @@ def test_affine_message_decomposition_equals_per_edge_linear():
     lay.load_state_dict(g["state_dict"])
     x, ei = g["x"], g["edge_index"]
     with torch.no_grad():
-        U, V = lay._affine_terms(x)
+        U, V = lay._affine_terms(x, lay.F_in)
         xt = x.view(-1, lay.towers, lay.F_in)
         h = torch.cat([xt[ei[1]], xt[ei[0]]], -1)
         msg = torch.stack([nn(h[:, t]) for t, nn in enumerate(lay.pre_nns)], 1).reshape(ei.size(1), -1)
