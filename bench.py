@@ -252,6 +252,18 @@ def run_ours(args):
             y = lay(x_dev, ei_dev)              # new edge_index tensor -> the CSR is rebuilt inside the call
         outh.copy_(y, non_blocking=True)
 
+    # PCIe health of this box (context for e2e: the layer call moves 192 MB per step over PCIe)
+    def copy_rate(fn, nbytes):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        return nbytes / (a.elapsed_time(b) * 1e-3) / 1e9
+    xdev_tmp = torch.empty_like(xd)
+    h2d_gbs = copy_rate(lambda: xdev_tmp.copy_(xh, non_blocking=True), xh.numel() * 4)
+    ydev_tmp = torch.empty((n, f), dtype=torch.float32, device=dev)
+    d2h_gbs = copy_rate(lambda: outh.copy_(ydev_tmp, non_blocking=True), n * f * 4)
+    del xdev_tmp, ydev_tmp
+
     k2 = max(3, min(args.steps, 20))
     for _ in range(3):
         e2e_step()
@@ -301,6 +313,8 @@ def run_ours(args):
         "csr_build_ms": {"first_call": csr_ms_first, "steady": csr_ms},
         "e2e": {"value": e / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": x.numel() * 4 + ei.numel() * 8, "d2h_bytes_per_step": n * f * 4,
+                "device_ms_per_step": s2.elapsed_time(e2) / k2, "wall_ms_per_step": e2e_wall_ms,
+                "pcie_h2d_gbs": h2d_gbs, "pcie_d2h_gbs": d2h_gbs, "pinned": bool(xh.is_pinned() and outh.is_pinned()),
                 "what": "PNAConvSimple.forward(x, edge_index) from pinned host tensors: H2D + CSR build + aggregate + post-MLP + D2H"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
