@@ -80,3 +80,27 @@ def test_synthetic_configs_have_the_stated_shapes():
     assert x.shape == (300, 16)
     b = synth.algorithmic_bytes(169343, 1166243, 128, 4, 1536)
     assert abs(b["b_min"] / 1e9 - 1.13) < 0.01 and abs(b["b_gather"] / 1e9 - 1.64) < 0.01
+
+
+def test_padding_algebra_is_exact_on_the_oracle():
+    """Zero-padded feature blocks + zero weight columns reproduce the unpadded layer output exactly (pna_b200/padding.py)."""
+    from oracle import pna_oracle as O
+    from pna_b200 import padding as pad
+    torch.manual_seed(0)
+    n, e, f = 60, 300, 15
+    fp = pad.padded_width(f, torch.float32)
+    assert fp == 16 and pad.padded_width(75, torch.bfloat16) == 80 and pad.padded_width(128, torch.float32) == 128
+    x, ei = torch.randn(n, f), torch.randint(0, n, (2, e))
+    A, S = ["mean", "max", "min", "std"], ["identity", "amplification", "attenuation"]
+    avg = O.avg_deg_from_histogram(torch.bincount(torch.bincount(ei[1], minlength=n)))
+    W, b = torch.randn(7, 12 * f), torch.randn(7)
+    ref = torch.nn.functional.linear(O.simple_propagate(x, ei, A, S, avg), W, b)
+    got = torch.nn.functional.linear(O.simple_propagate(pad.pad_cols(x, fp), ei, A, S, avg),
+                                     pad.expand_weight_cols(W, 12, f, fp), b)
+    assert torch.equal(ref, got)
+    # tower blocks
+    xt = torch.randn(n, 3 * f)
+    p = pad.pad_blocks(xt, 3, f, fp)
+    assert p.shape == (n, 3 * fp) and torch.equal(p.view(n, 3, fp)[:, :, :f], xt.view(n, 3, f)) and float(p.view(n, 3, fp)[:, :, f:].abs().sum()) == 0
+    Wr = pad.expand_weight_rows(torch.randn(f, 9), f, fp)
+    assert Wr.shape == (fp, 9) and float(Wr[f:].abs().sum()) == 0

@@ -43,7 +43,15 @@ def run(name, ei, x, check_rows=2000):
     tol = dict(rtol=1e-5, atol=1e-5) if x.dtype == torch.float32 else dict(rtol=2 ** -8, atol=1e-3)
     ok = torch.allclose(got[light], want[light], **tol)
     by = synth.algorithmic_bytes(n, e, f, x.element_size(), 12 * f)
-    rec = {"config": name, "n_nodes": n, "n_edges": e, "n_feat": f, "dtype": str(x.dtype).replace("torch.", ""), "ms": ms,
+    # backward of the aggregation (pna_aggregate_bwd), same graph, upstream gradient of ones
+    go = torch.ones_like(out)
+    tb = []
+    for i in range(5):
+        flush.zero_()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); pna_b200.aggregate.aggregate_backward(go, xd, csr, A4, S3, avg); t.record(); torch.cuda.synchronize()
+        if i >= 1: tb.append(s.elapsed_time(t))
+    rec = {"config": name, "backward_ms": statistics.median(tb), "n_nodes": n, "n_edges": e, "n_feat": f, "dtype": str(x.dtype).replace("torch.", ""), "ms": ms,
            "edges_per_s": e / ms * 1e3, "b_min_gbs": by["b_min"] / ms / 1e6, "frac_of_measured_peak": by["b_min"] / ms / 1e6 / peak,
            "split_rows": csr.n_hubs, "max_in_degree": csr.max_degree, "parity_first_rows": bool(ok)}
     print(json.dumps(rec), flush=True)
@@ -59,5 +67,21 @@ ei, x, _ = synth.zinc_like(dtype=torch.bfloat16); recs.append(run("3 ZINC-like 1
 ei, x, _ = synth.zinc_like(n_feat=80, dtype=torch.bfloat16); recs.append(run("3p ZINC-like, feature pitch padded to F=80 bf16", ei, x))
 ei, x = synth.superpixel_like(); recs.append(run("4 superpixels 15k graphs (one GPU's share) F=64 fp32", ei, x))
 ei, x = synth.powerlaw(); recs.append(run("5 power-law 1.25M/12.5M (one GPU's share) F=256 fp32", ei, x))
+# layer level on ZINC-like dims: PNAConv(75 -> 75, towers 5) fp32, odd tower width 15 -> padded to 16 inside the layer
+ei, x, _ = synth.zinc_like(dtype=torch.float32)
+n = x.size(0)
+lay = pna_b200.PNAConv(75, 75, A4, S3, synth.degree_histogram(ei[1], n), towers=5, divide_input=True).to(dev)
+xd, eid = x.to(dev), ei.to(dev)
+csr = pna_b200.build_csr(eid[0], eid[1], n)
+with torch.no_grad():
+    for _ in range(3): lay(xd, eid, csr=csr)
+    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(20): lay(xd, eid, csr=csr)
+    t.record(); torch.cuda.synchronize()
+rec = {"config": "3L ZINC-like PNAConv(75,75,towers=5) layer forward fp32, CSR cached", "n_nodes": n, "n_edges": ei.size(1),
+       "ms": s.elapsed_time(t) / 20, "edges_per_s": ei.size(1) / (s.elapsed_time(t) / 20) * 1e3}
+print(json.dumps(rec), flush=True)
+recs.append(rec)
 if args.out:
     json.dump(recs, open(args.out, "w"), indent=1)
