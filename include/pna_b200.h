@@ -178,7 +178,8 @@ typedef struct pna_agg {
   const int32_t* chunk_items;
   int64_t n_hubs;
   int64_t n_chunks;
-  float* hub_partials;       /* fp32 scratch [n_chunks * 4 * n_feat]; may be NULL when n_hubs == 0 */
+  float* hub_partials;       /* fp32 scratch [n_chunks * 4 * n_feat] (pna_aggregate_bwd: [(n_chunks + n_hubs) * 6 * n_feat]);
+                                may be NULL when n_hubs == 0 */
   const int32_t* row_ids;    /* nullable [n_row_ids]: process only these light rows (halo overlap); hubs unaffected.
                                 With a light view, view row i is output row row_ids[i]. */
   int64_t n_row_ids;

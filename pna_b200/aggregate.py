@@ -175,7 +175,12 @@ def aggregate_backward(grad_out: torch.Tensor, gathered: torch.Tensor, csr: CSRG
         n_aggr=n_aggr, aggr_codes=aggr_codes, n_scalers=n_scal, scaler_codes=scal_codes,
         avg_log=float(avg_deg["log"]), avg_lin=float(avg_deg.get("lin", 1.0)),
         split_threshold=csr.split_threshold, chunk_edges=csr.chunk_edges,
-        hub_info=_ptr(csr.hub_info) if csr.n_hubs else None, n_hubs=csr.n_hubs, n_chunks=csr.n_chunks)
+        hub_info=_ptr(csr.hub_info) if csr.n_hubs else None, chunk_items=_ptr(csr.chunk_items) if csr.n_hubs else None,
+        n_hubs=csr.n_hubs, n_chunks=csr.n_chunks)
+    scratch = None
+    if csr.n_hubs:   # per-chunk statistics + per-split-row coefficients
+        scratch = torch.empty(((csr.n_chunks + csr.n_hubs) * 6, F), dtype=torch.float32, device=dev)
+        d.hub_partials = scratch.data_ptr()
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().pna_aggregate_bwd(C.byref(d), grad_out.data_ptr(), grad_out.stride(0) if N > 1 else grad_out.size(1),
                                                 gg.data_ptr(), F, _ptr(gb), F, torch.cuda.current_stream(dev).cuda_stream))

@@ -8,7 +8,8 @@
 // so that  grad_m(slot) = c0 + c1 * m + [slot == argmin] g_min + [slot == argmax] g_max  with two per-row coefficients.
 // Two passes over the slots of a row: (A) recompute sum, sumsq, min, max and the first arg slots exactly as the forward
 // does; (C) evaluate grad_m per slot, accumulate it into grad_gathered[col[slot]] (vector atomics -- several
-// destinations share a source) and into grad_row_bias[row].  Rows at/above the split threshold get one CTA each.
+// destinations share a source) and into grad_row_bias[row].  Rows at/above the split threshold are processed chunk by
+// chunk by three small kernels (statistics, coefficients, scatter), like the forward.
 #include "pna_aggregate.cuh"
 #include <string.h>
 
@@ -162,28 +163,55 @@ __global__ void __launch_bounds__(kBwdThreads) k_bwd_rows(const BParams b) {
     }
     return;
   }
+  constexpr int UB = 4;   // neighbour rows in flight per lane in each pass
   Stats<VEC> st;
   st.init();
-  for (int e = beg; e < end; ++e) {
-    float m[VEC];
-    load_m<T, VEC>(p, p.col ? __ldg(p.col + e) : e, lc.f, bias, has_bias, m);
-    st.add(m, e);
+  for (int e = beg; e < end; e += UB) {
+    int src[UB];
+    typename Io<T, VEC>::Raw raw[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) src[u] = (e + u < end) ? (p.col ? __ldg(p.col + e + u) : e + u) : -1;
+#pragma unroll
+    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(gathered_row<T>(p, src[u]) + lc.f);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      if (src[u] >= 0) {
+        float m[VEC];
+        Io<T, VEC>::unpack(raw[u], m);
+        if (has_bias) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) m[i] = __fadd_rn(m[i], bias[i]);
+        }
+        st.add(m, e + u);
+      }
+    }
   }
   Coef<VEC> c;
   coefficients<T, VEC>(b, row, deg, lc.ooff, st, c);
   float gbs[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) gbs[i] = 0.f;
-  for (int e = beg; e < end; ++e) {
-    const int src = p.col ? __ldg(p.col + e) : e;
-    float m[VEC], gm[VEC];
-    load_m<T, VEC>(p, src, lc.f, bias, has_bias, m);
+  for (int e = beg; e < end; e += UB) {
+    int src[UB];
+    typename Io<T, VEC>::Raw raw[UB];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      gm[i] = c.c0[i] + c.c1[i] * m[i] + (e == st.amn[i] ? c.gmin[i] : 0.f) + (e == st.amx[i] ? c.gmax[i] : 0.f);
-      gbs[i] += gm[i];
+    for (int u = 0; u < UB; ++u) src[u] = (e + u < end) ? (p.col ? __ldg(p.col + e + u) : e + u) : -1;
+#pragma unroll
+    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(gathered_row<T>(p, src[u]) + lc.f);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      if (src[u] >= 0) {
+        float m[VEC], gm[VEC];
+        Io<T, VEC>::unpack(raw[u], m);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          if (has_bias) m[i] = __fadd_rn(m[i], bias[i]);
+          gm[i] = c.c0[i] + c.c1[i] * m[i] + (e + u == st.amn[i] ? c.gmin[i] : 0.f) + (e + u == st.amx[i] ? c.gmax[i] : 0.f);
+          gbs[i] += gm[i];
+        }
+        scatter_grad<VEC>(b, src[u], lc.f, gm, p.col != nullptr);
+      }
     }
-    scatter_grad<VEC>(b, src, lc.f, gm, p.col != nullptr);
   }
   if (b.gb) {
 #pragma unroll
@@ -191,87 +219,149 @@ __global__ void __launch_bounds__(kBwdThreads) k_bwd_rows(const BParams b) {
   }
 }
 
-// ---- split rows: one CTA per row, NG lane groups over contiguous slot ranges, statistics merged in shared memory ----
-constexpr int kBwdGroups = 8;
-
+// ---- split rows: chunk-parallel, like the forward ---------------------------------------------------------------
+// (1) k_bwd_hub_stats: one lane group per 128-slot chunk -> partial sum, sumsq, min, max, first argmin / argmax slot;
+// (2) k_bwd_hub_coef:  one lane group per split row merges its chunks in chunk order (strict < keeps the first slot)
+//                      and turns the upstream gradient into (c0, c1, gmin, gmax, argmin, argmax) per feature;
+// (3) k_bwd_hub_scatter: one lane group per chunk evaluates grad_m per slot, scatters it, and adds its share of the
+//                      row_bias gradient.  Scratch (descriptor field hub_partials): 6*F floats per chunk + per split row.
 template <typename T, int VEC, int G>
-__global__ void __launch_bounds__(kBwdGroups * 32) k_bwd_hubs(const BParams b) {
+__global__ void __launch_bounds__(kBwdThreads) k_bwd_hub_stats(const BParams b) {
   const KParams& p = b.k;
-  extern __shared__ float sm[];
-  constexpr int W = G * VEC;                   // columns of this feature block
-  float* s_sum = sm;                           // [NG][W] each
-  float* s_sq = s_sum + kBwdGroups * W;
-  float* s_mn = s_sq + kBwdGroups * W;
-  float* s_mx = s_mn + kBwdGroups * W;
-  int* s_amn = reinterpret_cast<int*>(s_mx + kBwdGroups * W);
-  int* s_amx = s_amn + kBwdGroups * W;
-  const int gl = threadIdx.x % G, q = threadIdx.x / G;
-  const long long h = blockIdx.x;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane % G;
+  const long long c = ((long long)blockIdx.x * (kBwdThreads / 32) + (threadIdx.x >> 5)) * RPW + lane / G;
+  if (c >= p.n_chunks) return;
+  const LaneCols lc = lane_cols<VEC>(p, gl, blockIdx.y * (G * VEC));
+  if (!lc.ok) return;
+  const int h = __ldg(p.chunk_items + 2 * c), j = __ldg(p.chunk_items + 2 * c + 1);
   const long long row = __ldg(p.hub_info + 4 * h);
-  const int deg = __ldg(p.hub_info + 4 * h + 3);
-  const int beg = __ldg(p.rowptr + row);
-  const LaneCols lc = lane_cols<VEC>(p, gl, blockIdx.y * W);
+  const int rbeg = __ldg(p.rowptr + row), rend = __ldg(p.rowptr + row + 1);
+  const int beg = rbeg + j * p.chunk, end = min(beg + p.chunk, rend);
   const bool has_bias = p.bias != nullptr;
   float bias[VEC];
-  if (has_bias && lc.ok) Io<T, VEC>::load(static_cast<const T*>(p.bias) + row * p.ldb + lc.f, bias);
-  const int per = (deg + kBwdGroups - 1) / kBwdGroups;
-  const int e0 = beg + q * per, e1 = min(beg + deg, e0 + per);
+  if (has_bias) Io<T, VEC>::load(static_cast<const T*>(p.bias) + row * p.ldb + lc.f, bias);
+  constexpr int UB = 4;
   Stats<VEC> st;
   st.init();
-  if (lc.ok) {
-    for (int e = e0; e < e1; ++e) {
-      float m[VEC];
-      load_m<T, VEC>(p, p.col ? __ldg(p.col + e) : e, lc.f, bias, has_bias, m);
-      st.add(m, e);
-    }
+  for (int e = beg; e < end; e += UB) {
+    int src[UB];
+    typename Io<T, VEC>::Raw raw[UB];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int o = q * W + gl * VEC + i;
-      s_sum[o] = st.sum[i]; s_sq[o] = st.sq[i]; s_mn[o] = st.mn[i]; s_mx[o] = st.mx[i]; s_amn[o] = st.amn[i]; s_amx[o] = st.amx[i];
-    }
-  }
-  __syncthreads();
-  Coef<VEC> c;
-  if (lc.ok) {
-    st.init();
-    for (int g = 0; g < kBwdGroups; ++g) {      // groups hold increasing slot ranges: strict < keeps the first attaining slot
+    for (int u = 0; u < UB; ++u) src[u] = (e + u < end) ? (p.col ? __ldg(p.col + e + u) : e + u) : -1;
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const int o = g * W + gl * VEC + i;
-        st.sum[i] += s_sum[o]; st.sq[i] += s_sq[o];
-        if (s_mn[o] < st.mn[i]) { st.mn[i] = s_mn[o]; st.amn[i] = s_amn[o]; }
-        if (s_mx[o] > st.mx[i]) { st.mx[i] = s_mx[o]; st.amx[i] = s_amx[o]; }
+    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(gathered_row<T>(p, src[u]) + lc.f);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      if (src[u] >= 0) {
+        float m[VEC];
+        Io<T, VEC>::unpack(raw[u], m);
+        if (has_bias) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) m[i] = __fadd_rn(m[i], bias[i]);
+        }
+        st.add(m, e + u);
       }
     }
-    coefficients<T, VEC>(b, row, deg, lc.ooff, st, c);
   }
-  __syncthreads();   // s_sum is reused for the row_bias gradient below
+  float* part = p.partials + c * 6ll * p.F + lc.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    part[0ll * p.F + i] = st.sum[i]; part[1ll * p.F + i] = st.sq[i]; part[2ll * p.F + i] = st.mn[i]; part[3ll * p.F + i] = st.mx[i];
+    part[4ll * p.F + i] = __int_as_float(st.amn[i]); part[5ll * p.F + i] = __int_as_float(st.amx[i]);
+  }
+}
+
+template <typename T, int VEC, int G>
+__global__ void __launch_bounds__(kBwdThreads) k_bwd_hub_coef(const BParams b) {
+  const KParams& p = b.k;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane % G;
+  const long long h = ((long long)blockIdx.x * (kBwdThreads / 32) + (threadIdx.x >> 5)) * RPW + lane / G;
+  if (h >= p.n_hubs) return;
+  const LaneCols lc = lane_cols<VEC>(p, gl, blockIdx.y * (G * VEC));
+  if (!lc.ok) return;
+  const long long row = __ldg(p.hub_info + 4 * h);
+  const int first = __ldg(p.hub_info + 4 * h + 1), nch = __ldg(p.hub_info + 4 * h + 2), deg = __ldg(p.hub_info + 4 * h + 3);
+  Stats<VEC> st;
+  st.init();
+  for (int j = 0; j < nch; ++j) {
+    const float* part = p.partials + (long long)(first + j) * 6ll * p.F + lc.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      st.sum[i] += part[0ll * p.F + i]; st.sq[i] += part[1ll * p.F + i];
+      const float mn = part[2ll * p.F + i], mx = part[3ll * p.F + i];
+      if (mn < st.mn[i]) { st.mn[i] = mn; st.amn[i] = __float_as_int(part[4ll * p.F + i]); }
+      if (mx > st.mx[i]) { st.mx[i] = mx; st.amx[i] = __float_as_int(part[5ll * p.F + i]); }
+    }
+  }
+  Coef<VEC> c;
+  coefficients<T, VEC>(b, row, deg, lc.ooff, st, c);
+  float* co = p.partials + (p.n_chunks + h) * 6ll * p.F + lc.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    co[0ll * p.F + i] = c.c0[i]; co[1ll * p.F + i] = c.c1[i]; co[2ll * p.F + i] = c.gmin[i]; co[3ll * p.F + i] = c.gmax[i];
+    co[4ll * p.F + i] = __int_as_float(st.amn[i]); co[5ll * p.F + i] = __int_as_float(st.amx[i]);
+  }
+  if (b.gb) {   // the chunks add their shares atomically in pass 3
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) b.gb[row * b.ldgb + lc.f + i] = 0.f;
+  }
+}
+
+template <typename T, int VEC, int G>
+__global__ void __launch_bounds__(kBwdThreads) k_bwd_hub_scatter(const BParams b) {
+  const KParams& p = b.k;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane % G;
+  const long long c = ((long long)blockIdx.x * (kBwdThreads / 32) + (threadIdx.x >> 5)) * RPW + lane / G;
+  if (c >= p.n_chunks) return;
+  const LaneCols lc = lane_cols<VEC>(p, gl, blockIdx.y * (G * VEC));
+  if (!lc.ok) return;
+  const int h = __ldg(p.chunk_items + 2 * c), j = __ldg(p.chunk_items + 2 * c + 1);
+  const long long row = __ldg(p.hub_info + 4 * h);
+  const int rbeg = __ldg(p.rowptr + row), rend = __ldg(p.rowptr + row + 1);
+  const int beg = rbeg + j * p.chunk, end = min(beg + p.chunk, rend);
+  const bool has_bias = p.bias != nullptr;
+  float bias[VEC];
+  if (has_bias) Io<T, VEC>::load(static_cast<const T*>(p.bias) + row * p.ldb + lc.f, bias);
+  const float* co = p.partials + (p.n_chunks + h) * 6ll * p.F + lc.f;
+  Coef<VEC> cf;
+  int amn[VEC], amx[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    cf.c0[i] = co[0ll * p.F + i]; cf.c1[i] = co[1ll * p.F + i]; cf.gmin[i] = co[2ll * p.F + i]; cf.gmax[i] = co[3ll * p.F + i];
+    amn[i] = __float_as_int(co[4ll * p.F + i]); amx[i] = __float_as_int(co[5ll * p.F + i]);
+  }
+  constexpr int UB = 4;
   float gbs[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) gbs[i] = 0.f;
-  if (lc.ok) {
-    for (int e = e0; e < e1; ++e) {
-      const int src = p.col ? __ldg(p.col + e) : e;
-      float m[VEC], gm[VEC];
-      load_m<T, VEC>(p, src, lc.f, bias, has_bias, m);
+  for (int e = beg; e < end; e += UB) {
+    int src[UB];
+    typename Io<T, VEC>::Raw raw[UB];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        gm[i] = c.c0[i] + c.c1[i] * m[i] + (e == st.amn[i] ? c.gmin[i] : 0.f) + (e == st.amx[i] ? c.gmax[i] : 0.f);
-        gbs[i] += gm[i];
+    for (int u = 0; u < UB; ++u) src[u] = (e + u < end) ? (p.col ? __ldg(p.col + e + u) : e + u) : -1;
+#pragma unroll
+    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(gathered_row<T>(p, src[u]) + lc.f);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      if (src[u] >= 0) {
+        float m[VEC], gm[VEC];
+        Io<T, VEC>::unpack(raw[u], m);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          if (has_bias) m[i] = __fadd_rn(m[i], bias[i]);
+          gm[i] = cf.c0[i] + cf.c1[i] * m[i] + (e + u == amn[i] ? cf.gmin[i] : 0.f) + (e + u == amx[i] ? cf.gmax[i] : 0.f);
+          gbs[i] += gm[i];
+        }
+        scatter_grad<VEC>(b, src[u], lc.f, gm, p.col != nullptr);
       }
-      scatter_grad<VEC>(b, src, lc.f, gm, p.col != nullptr);
     }
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) s_sum[q * W + gl * VEC + i] = gbs[i];
   }
-  __syncthreads();
-  if (b.gb && lc.ok && q == 0) {
+  if (b.gb) {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      float t = 0.f;
-      for (int g = 0; g < kBwdGroups; ++g) t += s_sum[g * W + gl * VEC + i];
-      b.gb[row * b.ldgb + lc.f + i] = t;
-    }
+    for (int i = 0; i < VEC; ++i) atomicAdd(b.gb + row * b.ldgb + lc.f + i, gbs[i]);
   }
 }
 
@@ -286,8 +376,12 @@ static int launch_bwd(const BParams& b, cudaStream_t st) {
   k_bwd_rows<T, VEC, G><<<dim3((unsigned)gx, gy), kBwdThreads, 0, st>>>(b);
   PNA_CUDA_TRY(cudaGetLastError());
   if (p.n_hubs > 0) {
-    const size_t smem = (size_t)kBwdGroups * G * VEC * 6 * sizeof(float);
-    k_bwd_hubs<T, VEC, G><<<dim3((unsigned)p.n_hubs, gy), kBwdGroups * G, smem, st>>>(b);
+    const long long gc = (p.n_chunks + per_block - 1) / per_block, gh = (p.n_hubs + per_block - 1) / per_block;
+    k_bwd_hub_stats<T, VEC, G><<<dim3((unsigned)gc, gy), kBwdThreads, 0, st>>>(b);
+    PNA_CUDA_TRY(cudaGetLastError());
+    k_bwd_hub_coef<T, VEC, G><<<dim3((unsigned)gh, gy), kBwdThreads, 0, st>>>(b);
+    PNA_CUDA_TRY(cudaGetLastError());
+    k_bwd_hub_scatter<T, VEC, G><<<dim3((unsigned)gc, gy), kBwdThreads, 0, st>>>(b);
     PNA_CUDA_TRY(cudaGetLastError());
   }
   return PNA_OK;
@@ -322,7 +416,9 @@ extern "C" int pna_aggregate_bwd(const pna_agg_t* d, const void* grad_out, int64
   PNA_REQUIRE(d->gathered && d->rowptr && grad_out && grad_gathered, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: null pointer");
   PNA_REQUIRE(d->peer_gathered == nullptr, PNA_ERR_UNSUPPORTED, "pna_aggregate_bwd: peer-memory graphs are forward-only");
   PNA_REQUIRE(d->split_threshold >= 2, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: bad split threshold");
-  if (d->n_hubs > 0) PNA_REQUIRE(d->hub_info != nullptr, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: hub_info missing");
+  if (d->n_hubs > 0)
+    PNA_REQUIRE(d->hub_info && d->chunk_items && d->hub_partials && d->chunk_edges >= 1, PNA_ERR_BAD_ARG,
+                "pna_aggregate_bwd: split rows need hub_info, chunk_items and hub_partials ((n_chunks + n_hubs) * 6 * n_feat floats)");
 
   BParams b;
   memset(&b, 0, sizeof(b));
@@ -337,7 +433,8 @@ extern "C" int pna_aggregate_bwd(const pna_agg_t* d, const void* grad_out, int64
   p.Wt = (p.has_self + p.nA * p.nS) * p.Ft;
   p.avg_log = d->avg_log; p.avg_lin = d->avg_lin;
   p.flags = d->flags; p.split = d->split_threshold; p.chunk = d->chunk_edges;
-  p.hub_info = d->hub_info; p.n_hubs = d->n_hubs;
+  p.hub_info = d->hub_info; p.n_hubs = d->n_hubs; p.chunk_items = d->chunk_items; p.n_chunks = d->n_chunks;
+  p.partials = d->hub_partials;
   b.go = grad_out; b.ldgo = ld_grad_out;
   b.gg = grad_gathered; b.ldgg = ld_grad_gathered;
   b.gb = grad_row_bias; b.ldgb = ld_grad_row_bias;
