@@ -59,7 +59,7 @@ class ClockSampler:
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -220,9 +220,19 @@ def run_ours(args):
         torch.cuda.synchronize()
         return [s.elapsed_time(t) for s, t in zip(starts, ends)]
 
+    # clocks / throttle reasons are sampled (20 Hz) while the GPU runs this workload: the timed steps themselves last
+    # only ~15 ms, so the sampler brackets them with extra untimed passes of the same kernels to collect enough samples
     with ClockSampler(local) as clk:
+        time.sleep(0.06)
+        t_end = time.perf_counter() + 0.5
+        while time.perf_counter() < t_end:
+            step()
+        torch.cuda.synchronize()
         per_step = timed(args.steps, args.warmup)
-        time.sleep(0.15)
+        t_end = time.perf_counter() + 0.5
+        while time.perf_counter() < t_end:
+            step()
+        torch.cuda.synchronize()
     clocks = clk.summary()
     t_ms = sum(per_step) / len(per_step)
     value = e / (t_ms * 1e-3)
