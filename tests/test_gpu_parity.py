@@ -544,3 +544,49 @@ def test_backward_bf16_runs_and_is_close(P, O):
     xm = x.to(dev()).requires_grad_(True)
     (P.pna_aggregate(xm, csr, aggrs, S3, avg).float() * w.to(dev())).sum().backward()
     torch.testing.assert_close(xm.grad.float().cpu(), xr.grad, rtol=5e-2, atol=5e-2)
+
+
+# ---- boundary properties: streams, CUDA graphs ----------------------------------------------------------------------
+def test_cuda_graph_capture_and_replay(P, O):
+    """A layer call enqueues on the caller's stream and never synchronises: it can be captured and replayed."""
+    n, e, f = 3000, 30000, 128
+    ei = rand_graph(n, e, seed=41, hub=2000)
+    avg = avg_deg_of(ei, n, O)
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+    x = torch.randn(n, f, device=dev())
+    out = torch.empty((n, 12 * f), device=dev())
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        P.aggregate_forward(x, csr, A4, S3, avg, out=out)          # warm-up outside capture (one-time occupancy query)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        P.aggregate_forward(x, csr, A4, S3, avg, out=out)
+    for seed in (1, 2):
+        x.copy_(torch.randn(n, f, generator=torch.Generator().manual_seed(seed)).to(dev()))
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        want = O.simple_propagate(x.cpu(), ei, A4, S3, avg)
+        light = torch.bincount(ei[1], minlength=n) < csr.split_threshold
+        torch.testing.assert_close(out.cpu()[light], want[light], **TOL)
+
+
+def test_two_streams_do_not_interfere(P, O):
+    n, e, f = 4000, 40000, 128
+    graphs = []
+    for s in (1, 2):
+        ei = rand_graph(n, e, seed=50 + s, hub=1500)
+        x = torch.randn(n, f, generator=torch.Generator().manual_seed(s))
+        graphs.append((ei, x, P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n), x.to(dev())))
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [None, None]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for k, (ei, x, csr, xd) in enumerate(graphs):
+            with torch.cuda.stream(streams[k]):
+                outs[k] = P.aggregate_forward(xd, csr, A4, S3, avg_deg_of(ei, n, O))
+    torch.cuda.synchronize()
+    for k, (ei, x, csr, xd) in enumerate(graphs):
+        assert_matches_reference(outs[k].cpu(), x, ei, csr, O, avg=avg_deg_of(ei, n, O))
