@@ -79,17 +79,58 @@ class PNAConvSimple(Module):
                 deg: Optional[Tensor] = None, csr: Optional[CSRGraph] = None) -> Tensor:
         # `deg` (precomputed in-degree) is accepted for signature compatibility with BASELINE.json's wording; the
         # in-degree always comes from the CSR row pointer, which is what degree(index) recounts in pna.py:247.
+        return self._post(self._aggregate_padded(x, _resolve_csr(x, edge_index, csr)), x.dtype)
+
+    def _aggregate_padded(self, x: Tensor, csr: CSRGraph) -> Tensor:
+        """Aggregation at the kernel's 16-byte feature granularity: odd widths (e.g. 75) run on zero-padded rows."""
         Fp = pad.padded_width(self.F_in, x.dtype)
+        return pna_aggregate(pad.pad_cols(x, Fp), csr, self.aggregators, self.scalers, self.avg_deg)
+
+    def _post(self, agg: Tensor, dtype) -> Tensor:
+        """post_nn on (a row block of) the aggregated tensor; padding is absorbed by zero columns of the first Linear."""
+        Fp = pad.padded_width(self.F_in, dtype)
         if Fp == self.F_in:
-            return self.post_nn(self.aggregate_only(x, edge_index, csr))
-        # odd width (e.g. 75): run the 128-bit path on zero-padded rows, absorb the padding in the first Linear
-        csr = _resolve_csr(x, edge_index, csr)
-        out = pna_aggregate(pad.pad_cols(x, Fp), csr, self.aggregators, self.scalers, self.avg_deg)
+            return self.post_nn(agg)
         blocks = len(self.aggregators) * len(self.scalers)
         lin0 = self.post_nn[0]
-        out = torch.nn.functional.linear(out, pad.expand_weight_cols(lin0.weight, blocks, self.F_in, Fp), lin0.bias)
+        out = torch.nn.functional.linear(agg, pad.expand_weight_cols(lin0.weight, blocks, self.F_in, Fp), lin0.bias)
         for m in list(self.post_nn)[1:]:
             out = m(out)
+        return out
+
+    @torch.no_grad()
+    def forward_host(self, x: Tensor, edge_index: Tensor, out: Optional[Tensor] = None, row_blocks: int = 8) -> Tensor:
+        """Inference entry point for HOST buffers (x, edge_index and the result live in pinned host memory), e.g. a
+        CPU-resident caller of the reference's loops.  Same result as ``forward``; the PCIe transfers are overlapped with
+        the device work instead of bracketing it:
+          * edge_index goes up first and the CSR is built while x is still in flight on a copy stream;
+          * after the aggregation, post_nn runs over row blocks and every finished block is copied back on a second
+            copy stream while the next block is being computed.
+        Returns the (pinned) host tensor; it is complete once the current stream has been synchronised."""
+        dev = next(self.parameters()).device
+        n = x.size(0)
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_host_streams") or self._host_streams[0].device != dev:
+            self._host_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s_in, s_out = self._host_streams
+        ei_d = edge_index.to(dev, non_blocking=True)
+        s_in.wait_stream(main)
+        with torch.cuda.stream(s_in):
+            x_d = x.to(dev, non_blocking=True)
+        csr = csr_from_edge_index(ei_d, n)                      # radix sort + views while x is on the wire
+        main.wait_stream(s_in)
+        x_d.record_stream(main)
+        agg = self._aggregate_padded(x_d, csr)
+        if out is None:
+            out = torch.empty((n, self.F_out), dtype=x.dtype, pin_memory=True)
+        step = max(1, (n + row_blocks - 1) // row_blocks)
+        for r0 in range(0, n, step):
+            y = self._post(agg[r0:r0 + step], x.dtype)
+            s_out.wait_stream(main)
+            with torch.cuda.stream(s_out):
+                out[r0:r0 + step].copy_(y, non_blocking=True)
+            y.record_stream(s_out)
+        main.wait_stream(s_out)
         return out
 
     def __repr__(self):

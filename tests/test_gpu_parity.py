@@ -590,3 +590,26 @@ def test_two_streams_do_not_interfere(P, O):
     torch.cuda.synchronize()
     for k, (ei, x, csr, xd) in enumerate(graphs):
         assert_matches_reference(outs[k].cpu(), x, ei, csr, O, avg=avg_deg_of(ei, n, O))
+
+
+@pytest.mark.parametrize("f", [128, 75])
+def test_forward_host_equals_forward(P, O, f):
+    """The host-buffer entry point (pinned in / pinned out, transfers overlapped) returns what forward returns."""
+    n, e = 5000, 40000
+    ei = rand_graph(n, e, seed=61, hub=1000)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(6))
+    deg = torch.bincount(torch.bincount(ei[1], minlength=n))
+    lay = P.PNAConvSimple(f, 32, A4, S3, deg, post_layers=2).to(dev())
+    with torch.no_grad():
+        want = lay(x.to(dev()), ei.to(dev())).cpu()
+    xh, eih = x.pin_memory(), ei.pin_memory()
+    for _ in range(2):                               # twice: streams / buffers are reused
+        got = lay.forward_host(xh, eih, row_blocks=5)
+        torch.cuda.synchronize()
+        assert got.is_pinned()
+        # row-blocked post-MLP: cuBLAS may pick another kernel for another M, so compare to rounding, not bit for bit
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+    ref = O.PNAConvSimpleOracle(f, 32, A4, S3, deg, post_layers=2)
+    ref.load_state_dict({k: v.cpu() for k, v in lay.state_dict().items()})
+    with torch.no_grad():
+        torch.testing.assert_close(got, ref(x, ei), **LAYER_TOL)
