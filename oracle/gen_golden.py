@@ -160,7 +160,13 @@ def dense_and_numpy_cases():
     lay.eval()
     with torch.no_grad():
         out = lay(h, adj)
-    save("dense_k1_k2", dict(kind="dense", adj=adj, h=h, avg_d=avg_d, k1=k1, k1_scaled=k1_scaled,
+    # gradients of a fixed scalar loss through the reference dense layer (multitask training path)
+    gw = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    hg = h.clone().requires_grad_(True)
+    lay.zero_grad()
+    (lay(hg, adj) * gw).sum().backward()
+    grads = dict(h=hg.grad.clone(), w=gw, params={k: v.grad.clone() for k, v in lay.named_parameters()})
+    save("dense_k1_k2", dict(kind="dense", adj=adj, h=h, avg_d=avg_d, k1=k1, k1_scaled=k1_scaled, grads=grads,
                              k2={k: torch.tensor(v) for k, v in k2.items()}, graph_type=str(gtype),
                              ctor=dict(in_features=f, out_features=f, towers=2, self_loop=False, pretrans_layers=1,
                                        posttrans_layers=1, divide_input=True),

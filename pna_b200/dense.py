@@ -103,6 +103,17 @@ class PNALayer(nn.Module):
             Wa, Wb = torch.cat(Wa, 0), torch.cat(Wb, 0)
         return h @ Wa.t(), h @ Wb.t(), b
 
+    def _second_call_columns(self, width, a2, device):
+        """bool [width]: output columns produced by the max/min call (per tower: self block, then S x A blocks of F_t)."""
+        T, Ft = len(self.towers), self.input_tower
+        A, S = len(self.aggregators), len(self.scalers)
+        m = torch.zeros(T, 1 + S * A, Ft, dtype=torch.bool)
+        for s_ in range(S):
+            for a_, name in enumerate(a2):
+                if name != "_skip":
+                    m[:, 1 + s_ * A + a_, :] = True
+        return m.reshape(-1)[:width].to(device)
+
     def forward(self, input, adj):
         B, N, Fin = input.shape
         graphs = dense_graphs(adj, self.self_loop)
@@ -115,15 +126,21 @@ class PNALayer(nn.Module):
         a2 = [a if a in _NBR_FIRST else "_skip" for a in self.aggregators]
         common = dict(towers=T, self_feat=h, self_divided=self.divide_input)
         need_grad = torch.is_grad_enabled() and (h.requires_grad or any(p.requires_grad for p in self.parameters()))
-        if need_grad:
-            raise NotImplementedError("dense adapter: autograd goes through the PyG / DGL signature layers")
-        # mean/std: message = W_first h_v + W_second h_u + b, neighbours u from row v of adj
-        out = aggregate_forward(Bm + b, graphs.row, a1, self.scalers, self.avg_d, row_bias=A, **common)
-        # max/min: message = W_first h_u + W_second h_v + b, neighbours u from column v of adj
-        if any(a != "_skip" for a in a2):
-            aggregate_forward(A + b, graphs.colwise, a2, self.scalers, self.avg_d, row_bias=Bm, out=out, **common)
-            # NB the scalers of the second call use the column degree; the reference scales every block with the ROW
-            # degree D = adj.sum(-1) (scalers.py:13,21).  They coincide for the symmetric adjacencies of the benchmark.
+        both = any(a != "_skip" for a in a2) and any(a != "_skip" for a in a1)
+        if not need_grad:
+            # mean/std: message = W_first h_v + W_second h_u + b, neighbours u from row v of adj
+            out = aggregate_forward(Bm + b, graphs.row, a1, self.scalers, self.avg_d, row_bias=A, **common)
+            # max/min: message = W_first h_u + W_second h_v + b, neighbours u from column v of adj; fills the skipped slots
+            if any(a != "_skip" for a in a2):
+                aggregate_forward(A + b, graphs.colwise, a2, self.scalers, self.avg_d, row_bias=Bm, out=out, **common)
+        else:
+            # training (multitask_benchmark/util/train.py:148): two differentiable calls, columns merged by a mask
+            out = pna_aggregate(Bm + b, graphs.row, a1, self.scalers, self.avg_d, row_bias=A, **common)
+            if any(a != "_skip" for a in a2):
+                out2 = pna_aggregate(A + b, graphs.colwise, a2, self.scalers, self.avg_d, row_bias=Bm, **common)
+                out = torch.where(self._second_call_columns(out.size(1), a2, h.device), out2, out) if both else out2
+        # NB the scalers of the second call use the column degree; the reference scales every block with the ROW
+        # degree D = adj.sum(-1) (scalers.py:13,21).  They coincide for the symmetric adjacencies of the benchmark.
         out = out.view(B * N, T, -1)
         y = torch.cat([tw.posttrans(out[:, t]) for t, tw in enumerate(self.towers)], dim=1)
         return self.mixing_network(y).view(B, N, -1)

@@ -613,3 +613,18 @@ def test_forward_host_equals_forward(P, O, f):
     ref.load_state_dict({k: v.cpu() for k, v in lay.state_dict().items()})
     with torch.no_grad():
         torch.testing.assert_close(got, ref(x, ei), **LAYER_TOL)
+
+
+def test_golden_dense_layer_backward(P):
+    """Training through the dense-adjacency adapter (multitask loop): gradients of the reference's dense layer."""
+    g = load_golden("dense_k1_k2")
+    lay = P.dense.PNALayer(aggregators=A4, scalers=S3, avg_d=g["avg_d"], **g["ctor"])
+    lay.load_state_dict(g["state_dict"])
+    lay = lay.to(dev()).eval()
+    h = g["h"].to(dev()).requires_grad_(True)
+    (lay(h, g["adj"].to(dev())) * g["grads"]["w"].to(dev())).sum().backward()
+    torch.testing.assert_close(h.grad.cpu(), g["grads"]["h"], rtol=1e-3, atol=5e-4)
+    for k, p in lay.named_parameters():
+        ref = g["grads"]["params"][k]
+        err = float((p.grad.cpu() - ref).norm() / ref.norm().clamp(min=1e-6))
+        assert err < 2e-3, f"{k}: {err:.2e}"
