@@ -151,7 +151,7 @@ CASES = [
     # n, e, F, hub
     (300, 2500, 128, 0), (300, 2500, 64, 0), (300, 2500, 16, 0), (257, 1900, 4, 0), (64, 400, 1, 0), (64, 400, 3, 0),
     (200, 1500, 75, 0), (200, 1500, 256, 0), (150, 900, 384, 0), (90, 700, 1024, 0), (120, 800, 130, 0),
-    (400, 3000, 128, 5000), (400, 3000, 32, 1500), (300, 1000, 75, 900), (128, 600, 512, 700),
+    (400, 3000, 128, 5000), (400, 3000, 32, 1500), (300, 1000, 75, 900), (128, 600, 512, 700), (150, 900, 160, 300),
 ]
 
 
@@ -628,3 +628,13 @@ def test_golden_dense_layer_backward(P):
         ref = g["grads"]["params"][k]
         err = float((p.grad.cpu() - ref).norm() / ref.norm().clamp(min=1e-6))
         assert err < 2e-3, f"{k}: {err:.2e}"
+
+
+def test_example_net_trains(P):
+    """examples/pyg_net.py: the reference's example network with the layer class swapped; loss must fall."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("pyg_net", os.path.join(os.path.dirname(os.path.dirname(__file__)), "examples", "pyg_net.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    losses = m.main(steps=25, n_graphs=600, verbose=False)
+    assert all(l == l and l < 1e6 for l in losses) and losses[-1] < 0.7 * losses[0]
