@@ -237,6 +237,7 @@ def run_ours(args):
     t_ms = sum(per_step) / len(per_step)
     value = e / (t_ms * 1e-3)
     launches_per_step = 1 + (1 if csr.n_hubs else 0)       # k_rows_stream (+ k_hub_finalize when rows were split)
+    # (the e2e / layer_fwd legs additionally launch k_split_weight + k_linear_3xtf32 and the CSR-build kernels)
 
     bytes_ = synth.algorithmic_bytes(n, e, f, 4, 12 * f)
     peak, peak_src = measured_peaks()
@@ -320,7 +321,7 @@ def run_ours(args):
                      "effective_gbs_b_gather": bytes_["b_gather"] / (t_ms * 1e-3) / 1e9},
         "kernels_ms": {"step_min": min(per_step), "step_median": statistics.median(per_step),
                        "kernels": "k_rows_stream (rows + chunks of split rows) + k_hub_finalize; per-kernel times: profiles/"},
-        "layer_fwd": {"ms": full_ms, "edges_per_s": e / (full_ms * 1e-3), "what": "PNAConvSimple.forward, CSR cached, post-MLP via cuBLAS"},
+        "layer_fwd": {"ms": full_ms, "edges_per_s": e / (full_ms * 1e-3), "what": "PNAConvSimple.forward, CSR cached: aggregation + post-MLP linear on the tensor cores (pna_linear_fwd, 3xTF32 tcgen05)"},
         "csr_build_ms": {"first_call": csr_ms_first, "steady": csr_ms},
         "e2e": {"value": e / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": x.numel() * 4 + ei.numel() * 8, "d2h_bytes_per_step": n * f * 4,

@@ -216,6 +216,16 @@ int pna_aggregate_bwd(const pna_agg_t* desc, const void* grad_out, int64_t ld_gr
 int pna_gather_rows(const void* src, int64_t ld_src, const int32_t* idx, int64_t n_idx, void* dst, int64_t ld_dst,
                     int32_t n_feat, int32_t dtype, pna_stream_t stream);
 
+/* ---- first dense linear of the post-aggregation MLP on the tensor cores (north_star: "the post-MLP uses tensor
+ * cores only for its dense linear"; reference pna.py:222-227 post_nn[0], models/dgl/pna_layer.py:31 posttrans) -----
+ * y[n_rows, n_out] = a[n_rows, n_in] . weight[n_out, n_in]^T + bias, fp32 in / fp32 out, fp32-accurate: every operand
+ * is split hi + lo and three tcgen05.mma kind::tf32 products (hi.hi + hi.lo + lo.hi) accumulate in TMEM, because plain
+ * TF32 (10-bit mantissa) cannot meet the 1e-5 parity bar.  n_in % 32 == 0, n_out in {64, 128, 256}; other shapes
+ * return PNA_ERR_UNSUPPORTED and the caller keeps its library GEMM.  workspace: 2 * n_in * n_out floats (split weight). */
+int pna_linear_workspace_bytes(int32_t n_in, int32_t n_out, size_t* bytes);
+int pna_linear_fwd(const float* a, int64_t lda, const float* weight, const float* bias, float* y, int64_t ldy, int64_t n_rows,
+                   int32_t n_in, int32_t n_out, void* workspace, size_t workspace_bytes, pna_stream_t stream);
+
 int pna_query(int what);
 const char* pna_last_error(void);
 

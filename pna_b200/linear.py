@@ -1,0 +1,65 @@
+"""First dense linear of the post-aggregation MLP on the B200 tensor cores (``pna_linear_fwd``, 3xTF32 tcgen05).
+
+``post_linear(a, weight, bias)`` is ``torch.nn.functional.linear`` for the shapes the kernel takes
+(fp32, in_features % 32 == 0, out_features in {64, 128, 256}) and falls back to the library GEMM for every other shape --
+the kernel is an accelerator for one GEMM shape family, not a requirement of the path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_OUT_OK = (64, 128, 256)
+
+
+def kernel_applies(a: torch.Tensor, weight: torch.Tensor) -> bool:
+    if os.environ.get("PNA_B200_TENSOR_LINEAR", "1") == "0":       # opt out: keep the library fp32 GEMM
+        return False
+    return (a.is_cuda and a.dtype == torch.float32 and weight.dtype == torch.float32 and a.dim() == 2 and a.size(0) > 0
+            and a.size(1) % 32 == 0 and weight.size(0) in _OUT_OK and a.stride(1) == 1 and a.stride(0) % 4 == 0
+            and a.data_ptr() % 16 == 0)
+
+
+def linear_tf32x3(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """y = a @ weight.T + bias through the C ABI (no autograd)."""
+    n, k = a.shape
+    o = weight.size(0)
+    dev = a.device
+    w = weight.detach().contiguous()
+    b = None if bias is None else bias.detach().contiguous()
+    y = torch.empty((n, o), dtype=torch.float32, device=dev)
+    ws = torch.empty(2 * k * o, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pna_linear_fwd(a.data_ptr(), a.stride(0), w.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(),
+                                             y.stride(0), n, k, o, ws.data_ptr(), ws.numel() * 4,
+                                             torch.cuda.current_stream(dev).cuda_stream))
+    return y
+
+
+class _Linear3xTF32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, weight, bias):
+        ctx.save_for_backward(a, weight)
+        ctx.has_bias = bias is not None
+        return linear_tf32x3(a, weight, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        a, weight = ctx.saved_tensors
+        ga = gy @ weight if ctx.needs_input_grad[0] else None
+        gw = gy.t() @ a if ctx.needs_input_grad[1] else None
+        gb = gy.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return ga, gw, gb
+
+
+def post_linear(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    if not kernel_applies(a, weight):
+        return torch.nn.functional.linear(a, weight, bias)
+    if torch.is_grad_enabled() and (a.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
+        return _Linear3xTF32.apply(a, weight, bias)
+    return linear_tf32x3(a, weight, bias)

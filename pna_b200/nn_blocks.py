@@ -48,7 +48,11 @@ class FCLayer(nn.Module):
 
     def forward(self, x, weight=None):
         """`weight`: optional replacement for linear.weight (same parameters, zero columns inserted for padded inputs)."""
-        h = self.linear(x) if weight is None else nn.functional.linear(x, weight, self.linear.bias)
+        if x.dim() == 2:   # tensor-core path for the shapes pna_linear_fwd takes, library GEMM otherwise
+            from .linear import post_linear
+            h = post_linear(x, self.linear.weight if weight is None else weight, self.linear.bias)
+        else:
+            h = self.linear(x) if weight is None else nn.functional.linear(x, weight, self.linear.bias)
         if self.activation is not None:
             h = self.activation(h)
         if self.dropout is not None:

@@ -15,6 +15,7 @@ from torch.nn import Linear, Module, ModuleList, ReLU, Sequential
 
 from . import padding as pad
 from .aggregate import avg_deg_from_histogram, pna_aggregate
+from .linear import post_linear
 from .csr import CSRGraph, csr_from_edge_index
 
 _AGGRS = ("sum", "mean", "min", "max", "var", "std")          # aggregators.py:35-42
@@ -89,11 +90,10 @@ class PNAConvSimple(Module):
     def _post(self, agg: Tensor, dtype) -> Tensor:
         """post_nn on (a row block of) the aggregated tensor; padding is absorbed by zero columns of the first Linear."""
         Fp = pad.padded_width(self.F_in, dtype)
-        if Fp == self.F_in:
-            return self.post_nn(agg)
         blocks = len(self.aggregators) * len(self.scalers)
         lin0 = self.post_nn[0]
-        out = torch.nn.functional.linear(agg, pad.expand_weight_cols(lin0.weight, blocks, self.F_in, Fp), lin0.bias)
+        # first Linear: tensor cores (3xTF32 tcgen05, pna_linear_fwd) when the shape allows, else the library GEMM
+        out = post_linear(agg, pad.expand_weight_cols(lin0.weight, blocks, self.F_in, Fp), lin0.bias)
         for m in list(self.post_nn)[1:]:
             out = m(out)
         return out

@@ -638,3 +638,38 @@ def test_example_net_trains(P):
     spec.loader.exec_module(m)
     losses = m.main(steps=25, n_graphs=600, verbose=False)
     assert all(l == l and l < 1e6 for l in losses) and losses[-1] < 0.7 * losses[0]
+
+
+# ---- tensor-core post-linear (pna_linear_fwd: 3xTF32 tcgen05) -------------------------------------------------------
+@pytest.mark.parametrize("n,k,o", [(1, 32, 64), (127, 64, 128), (1000, 96, 64), (4097, 1536, 128), (300, 320, 256)])
+def test_linear_3xtf32_matches_fp32(P, n, k, o):
+    from pna_b200 import linear as L
+    g = torch.Generator().manual_seed(n + k + o)
+    a = torch.randn(n, k, generator=g)
+    w = torch.randn(o, k, generator=g) / k ** 0.5
+    b = torch.randn(o, generator=g)
+    assert L.kernel_applies(a.to(dev()), w.to(dev()))
+    y = L.linear_tf32x3(a.to(dev()), w.to(dev()), b.to(dev())).cpu()
+    ref = (a.double() @ w.double().t() + b.double())
+    # the tensor core accumulates with truncation: ~0.5 ulp per 8-wide K step, so the bound scales with K
+    tol = 2e-6 + 2e-8 * k
+    assert float((y.double() - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max())), float((y.double() - ref).abs().max())
+    y2 = L.linear_tf32x3(a.to(dev()), w.to(dev()), None).cpu()
+    torch.testing.assert_close(y2, y - b, rtol=1e-6, atol=1e-6)
+
+
+def test_linear_autograd_and_fallback(P):
+    from pna_b200 import linear as L
+    a = torch.randn(200, 64, device=dev(), requires_grad=True)
+    w = torch.randn(128, 64, device=dev(), requires_grad=True)
+    b = torch.randn(128, device=dev(), requires_grad=True)
+    L.post_linear(a, w, b).square().sum().backward()
+    ga, gw, gb = a.grad.clone(), w.grad.clone(), b.grad.clone()
+    a.grad = w.grad = b.grad = None
+    torch.nn.functional.linear(a, w, b).square().sum().backward()
+    torch.testing.assert_close(ga, a.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(gw, w.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(gb, b.grad, rtol=1e-4, atol=1e-4)
+    odd = torch.randn(10, 30, device=dev())            # shape the kernel does not take: library GEMM
+    assert not L.kernel_applies(odd, torch.randn(7, 30, device=dev()))
+    assert L.post_linear(odd, torch.randn(7, 30, device=dev()), None).shape == (10, 7)
