@@ -7,7 +7,7 @@
 // tcgen05.mma kind::tf32 products are accumulated in TMEM:  hi.hi + hi.lo + lo.hi  (the dropped lo.lo term is 2^-22).
 //
 // One CTA per 128-row tile, 10 warps, 3-stage mbarrier ring of {A hi, A lo, W hi, W lo} tiles:
-//   warps 0-7  A loaders: coalesced 128-bit loads issued two K blocks ahead, split hi / lo (cvt.rna.tf32: an unbiased
+//   warps 0-7  A loaders: coalesced 128-bit loads issued four K blocks ahead, split hi / lo (cvt.rna.tf32: an unbiased
 //              split -- truncation accumulates its one-sided error linearly in K) and stored into the 128-byte-swizzled
 //              K-major layout UMMA reads (the operand has to pass through registers for the split, so no TMA here).
 //              Warps 0-3 are afterwards the epilogue: tcgen05.ld the accumulator, add the bias, store.
@@ -128,7 +128,8 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
     const int j = tid & 7;                                  // 16-byte unit inside the 128-byte K block row
     const int r_in = tid >> 3;                              // 0..31: row inside a 32-row slab
     constexpr int kSlabs = kLinM / 32;                      // 4
-    float4 pre0[kSlabs], pre1[kSlabs];                      // K blocks kb and kb+1, already in flight
+    constexpr int kAhead = 4;                               // K blocks of A kept in flight per thread (16 x 16 B)
+    float4 pre[kAhead][kSlabs];
     auto fetch = [&](int kb, float4 (&dst)[kSlabs]) {
 #pragma unroll
       for (int sl = 0; sl < kSlabs; ++sl) {
@@ -137,32 +138,35 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    fetch(0, pre0);
-    fetch(1, pre1);
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) fetch(u, pre[u]);
     unsigned phase = 0;
-    for (int kb = 0; kb < n_kb; ++kb) {
-      const int s = kb % kSt;
-      lin_mbar_wait(bars + 8 * (kSt + s), phase ^ 1);       // stage free
-      unsigned char* st = gbase + s * LinSmem<O>::kStage;
+    for (int kb0 = 0; kb0 < n_kb; kb0 += kAhead) {
 #pragma unroll
-      for (int sl = 0; sl < kSlabs; ++sl) {
-        const float4 v = pre0[sl];
-        float4 hi, lo;
-        hi.x = lin_tf32(v.x); lo.x = lin_tf32(v.x - hi.x);
-        hi.y = lin_tf32(v.y); lo.y = lin_tf32(v.y - hi.y);
-        hi.z = lin_tf32(v.z); lo.z = lin_tf32(v.z - hi.z);
-        hi.w = lin_tf32(v.w); lo.w = lin_tf32(v.w - hi.w);
-        const unsigned off = lin_swz(sl * 32 + r_in, j);    // quarter-warps write whole swizzled 128-byte rows: conflict free
-        *reinterpret_cast<float4*>(st + off) = hi;
-        *reinterpret_cast<float4*>(st + LinSmem<O>::kATile + off) = lo;
+      for (int u = 0; u < kAhead; ++u) {                    // unrolled so that pre[u] stays in registers
+        const int kb = kb0 + u;
+        if (kb >= n_kb) break;
+        const int s = kb % kSt;
+        lin_mbar_wait(bars + 8 * (kSt + s), phase ^ 1);     // stage free
+        unsigned char* st = gbase + s * LinSmem<O>::kStage;
+#pragma unroll
+        for (int sl = 0; sl < kSlabs; ++sl) {
+          const float4 v = pre[u][sl];
+          float4 hi, lo;
+          hi.x = lin_tf32(v.x); lo.x = lin_tf32(v.x - hi.x);
+          hi.y = lin_tf32(v.y); lo.y = lin_tf32(v.y - hi.y);
+          hi.z = lin_tf32(v.z); lo.z = lin_tf32(v.z - hi.z);
+          hi.w = lin_tf32(v.w); lo.w = lin_tf32(v.w - hi.w);
+          const unsigned off = lin_swz(sl * 32 + r_in, j);  // quarter-warps write whole swizzled 128-byte rows: conflict free
+          *reinterpret_cast<float4*>(st + off) = hi;
+          *reinterpret_cast<float4*>(st + LinSmem<O>::kATile + off) = lo;
+        }
+        fetch(kb + kAhead, pre[u]);                         // refill the slot just consumed
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) lin_mbar_arrive(bars + 8 * s);
+        if (s == kSt - 1) phase ^= 1;
       }
-#pragma unroll
-      for (int sl = 0; sl < kSlabs; ++sl) pre0[sl] = pre1[sl];
-      fetch(kb + 2, pre1);                                  // keep two K blocks of loads in flight
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to the MMA (async proxy)
-      __syncwarp();
-      if (lane == 0) lin_mbar_arrive(bars + 8 * s);
-      if (s == kSt - 1) phase ^= 1;
     }
     if (warp < 4) {
       // ---------------- epilogue ----------------
