@@ -83,6 +83,10 @@ __host__ __device__ __forceinline__ unsigned lin_swz(int r, int j) { return (uns
 template <int O>   // output width = UMMA_N, a multiple of 16 up to 256
 struct LinSmem {
   static constexpr int kSt = lin_stages(O);
+  // TMEM accumulators: kMain for hi.hi (K blocks dealt round-robin: fewer truncating accumulation steps and a smaller
+  // running sum per accumulator) + 1 for the two cross terms
+  static constexpr int kMain = (3 * O <= 512) ? 2 : 1;
+  static constexpr unsigned kCols = (kMain + 1) * O <= 64 ? 64 : (kMain + 1) * O <= 128 ? 128 : (kMain + 1) * O <= 256 ? 256 : 512;
   static constexpr int kATile = kLinM * 128;                  // bytes of one A hi (or lo) stage
   static constexpr int kWTile = O * 128;
   static constexpr int kStage = 2 * kATile + 2 * kWTile;
@@ -113,7 +117,7 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {   // TMEM: O columns (power of two >= 32)
-    constexpr unsigned cols = 2 * O <= 32 ? 32 : 2 * O <= 64 ? 64 : 2 * O <= 128 ? 128 : 2 * O <= 256 ? 256 : 512;
+    constexpr unsigned cols = LinSmem<O>::kCols;
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + 8 * (2 * kSt + 1)), "n"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -175,21 +179,27 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
       const long long row = row0 + warp * 32 + lane;        // TMEM lane = accumulator row; warp w owns lanes 32w..32w+31
 #pragma unroll
       for (int c0 = 0; c0 < O; c0 += 16) {
-        unsigned v[16], c[16];
+        unsigned v[16];
         const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
               "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
             : "r"(taddr));
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]), "=r"(c[8]), "=r"(c[9]),
-              "=r"(c[10]), "=r"(c[11]), "=r"(c[12]), "=r"(c[13]), "=r"(c[14]), "=r"(c[15])
-            : "r"(taddr + O));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(c[i]));
+        for (int acc = 1; acc <= LinSmem<O>::kMain; ++acc) {     // the other main accumulator(s) (only if K reached them) + cross terms
+          if (acc < LinSmem<O>::kMain && n_kb <= acc) continue;
+          unsigned c[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]), "=r"(c[8]), "=r"(c[9]),
+                "=r"(c[10]), "=r"(c[11]), "=r"(c[12]), "=r"(c[13]), "=r"(c[14]), "=r"(c[15])
+              : "r"(taddr + acc * O));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(c[i]));
+        }
         if (row < N) {
           float* yr = Y + row * ldy + c0;
 #pragma unroll
@@ -220,12 +230,14 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
 #pragma unroll
         for (int ks = 0; ks < kLinBK / 8; ++ks) {            // UMMA_K = 8 tf32 = 32 bytes along the swizzled row
           const unsigned ko = ks * 32;
-          // two accumulators: the tensor core adds into fp32 with truncation, a bias that grows with the number of
-          // accumulation steps times the magnitude of the running sum -- the two small cross terms (2^-11 of the main
-          // product) get their own accumulator so the main one takes K/8 steps instead of 3K/8
-          lin_mma_tf32(tmem + O, lin_desc(a_hi + ko), lin_desc(w_lo + ko), idesc, (kb | ks) ? 1u : 0u);
-          lin_mma_tf32(tmem + O, lin_desc(a_lo + ko), lin_desc(w_hi + ko), idesc, 1u);
-          lin_mma_tf32(tmem, lin_desc(a_hi + ko), lin_desc(w_hi + ko), idesc, (kb | ks) ? 1u : 0u);
+          // the tensor core adds into fp32 with truncation, a bias that grows with the number of accumulation steps
+          // times the magnitude of the running sum: the two small cross terms (2^-11 of the main product) get their own
+          // accumulator, and the main product alternates between kMain accumulators
+          constexpr int kMain = LinSmem<O>::kMain;
+          const unsigned corr = tmem + kMain * O, mainacc = tmem + (kb % kMain) * O;
+          lin_mma_tf32(corr, lin_desc(a_hi + ko), lin_desc(w_lo + ko), idesc, (kb | ks) ? 1u : 0u);
+          lin_mma_tf32(corr, lin_desc(a_lo + ko), lin_desc(w_hi + ko), idesc, 1u);
+          lin_mma_tf32(mainacc, lin_desc(a_hi + ko), lin_desc(w_hi + ko), idesc, (kb >= kMain || ks) ? 1u : 0u);
         }
         // release the stage when these MMAs have read it; after the last block also publish the accumulator
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bars + 8 * (kSt + s)) : "memory");
@@ -251,7 +263,7 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
   }
   __syncthreads();
   if (warp == 8) {
-    constexpr unsigned cols = 2 * O <= 32 ? 32 : 2 * O <= 64 ? 64 : 2 * O <= 128 ? 128 : 2 * O <= 256 ? 256 : 512;
+    constexpr unsigned cols = LinSmem<O>::kCols;
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(cols) : "memory");
   }
 }
