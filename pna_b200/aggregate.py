@@ -7,7 +7,6 @@ E x F message tensor (aggregators.py:9-32), three scaler passes (scalers.py:8-19
 from __future__ import annotations
 
 import ctypes as C
-import math
 from typing import Mapping, Optional, Sequence, Union
 
 import torch
@@ -130,27 +129,6 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
 
 
 # ---- autograd ----------------------------------------------------------------------------------------------------
-def _scaler_values(deg: torch.Tensor, scalers: list, avg_deg: Mapping[str, float]) -> torch.Tensor:
-    """[N, S] fp32 scaler values (scalers.py:8-29)."""
-    degf = deg.to(torch.float32)
-    lg = torch.log(degf + 1)
-    cols = []
-    for s in scalers:
-        if s == "identity":
-            cols.append(torch.ones_like(degf))
-        elif s == "amplification":
-            cols.append(lg / avg_deg["log"])
-        elif s == "attenuation":
-            cols.append(torch.where(degf == 0, torch.ones_like(degf), avg_deg["log"] / lg))
-        elif s == "linear":
-            cols.append(degf / avg_deg["lin"])
-        elif s == "inverse_linear":
-            cols.append(torch.where(degf == 0, torch.ones_like(degf), avg_deg["lin"] / degf))
-        else:
-            raise KeyError(s)
-    return torch.stack(cols, 1)
-
-
 def aggregate_backward(grad_out: torch.Tensor, gathered: torch.Tensor, csr: CSRGraph, aggregators: Names, scalers: Names,
                        avg_deg: Mapping[str, float], *, towers: int = 1, row_bias: Optional[torch.Tensor] = None,
                        has_self: bool = False, messages_in_csr_order: bool = False, need_bias_grad: bool = False):

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from .aggregate import aggregate_forward, pna_aggregate
-from .csr import CSRGraph, build_csr
+from .csr import build_csr
 from .nn_blocks import FCLayer, MLP
 
 _SELF_FIRST = ("mean", "std", "sum", "var")

@@ -6,7 +6,6 @@ the kernel is an accelerator for one GEMM shape family, not a requirement of the
 """
 from __future__ import annotations
 
-import ctypes as C
 import os
 from typing import Optional
 
