@@ -296,17 +296,21 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_wall_ms = 1e3 * (time.perf_counter() - t0) / k2
     e2e_ms = max(s2.elapsed_time(e2) / k2, e2e_wall_ms)      # host-side launch/sync time counts too
-    with torch.no_grad():
-        full_ms = None
-        s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(3):
-            lay(xd, eid, csr=csr)
-        s3.record()
-        for _ in range(20):
-            lay(xd, eid, csr=csr)
-        e3.record()
-        torch.cuda.synchronize()
-        full_ms = s3.elapsed_time(e3) / 20
+    def layer_ms():
+        with torch.no_grad():
+            s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                lay(xd, eid, csr=csr)
+            s3.record()
+            for _ in range(20):
+                lay(xd, eid, csr=csr)
+            e3.record()
+            torch.cuda.synchronize()
+            return s3.elapsed_time(e3) / 20
+    full_ms = layer_ms()                        # compact post path: [N, 4F] aggregate + pna_linear_scaled_fwd
+    os.environ["PNA_B200_COMPACT_POST"] = "0"
+    full_ms_12f = layer_ms()                    # the same layer through the materialised [N, 12F] tensor
+    del os.environ["PNA_B200_COMPACT_POST"]
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -328,7 +332,10 @@ def run_ours(args):
                      "effective_gbs_b_gather": bytes_["b_gather"] / (t_ms * 1e-3) / 1e9},
         "kernels_ms": {"step_min": min(per_step), "step_median": statistics.median(per_step),
                        "kernels": "k_rows_stream (rows + chunks of split rows) + k_hub_finalize; per-kernel times: profiles/"},
-        "layer_fwd": {"ms": full_ms, "edges_per_s": e / (full_ms * 1e-3), "what": "PNAConvSimple.forward, CSR cached: aggregation + post-MLP linear on the tensor cores (pna_linear_fwd, 3xTF32 tcgen05)"},
+        "layer_fwd": {"ms": full_ms, "edges_per_s": e / (full_ms * 1e-3), "ms_via_12f_tensor": full_ms_12f,
+                      "what": "PNAConvSimple.forward, CSR cached: aggregation with the identity scaler ([N,4F]) + post-MLP linear on "
+                              "the tensor cores regenerating the scaled copies in registers (pna_linear_scaled_fwd, 3xTF32 "
+                              "tcgen05); ms_via_12f_tensor = same layer through the materialised [N,12F] tensor"},
         "csr_build_ms": {"first_call": csr_ms_first, "steady": csr_ms},
         "e2e": {"value": e / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": x.numel() * 4 + ei.numel() * 8, "d2h_bytes_per_step": n * f * 4,

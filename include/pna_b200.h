@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNA_ABI_VERSION 4
+#define PNA_ABI_VERSION 5
 
 typedef void* pna_stream_t; /* a cudaStream_t / CUstream, passed opaquely */
 
@@ -225,6 +225,23 @@ int pna_gather_rows(const void* src, int64_t ld_src, const int32_t* idx, int64_t
 int pna_linear_workspace_bytes(int32_t n_in, int32_t n_out, size_t* bytes);
 int pna_linear_fwd(const float* a, int64_t lda, const float* weight, const float* bias, float* y, int64_t ldy, int64_t n_rows,
                    int32_t n_in, int32_t n_out, void* workspace, size_t workspace_bytes, pna_stream_t stream);
+
+/* ---- the same linear fed by the COMPACT aggregate (the [N, S*A*F] tensor is never written) --
+ * The reference's post-MLP input is cat over the scalers s of  scale_s(deg_i) * agg_i  (pna.py:247-249,
+ * scalers.py:8-29): S scaled copies of one [N, A*F] tensor.  With a = that tensor for the identity scaler alone
+ * (pna_aggregate_fwd with n_scalers = 1, scaler_codes = PNA_SCALE_IDENTITY) and row_scale[i, s] = the factor of scaler s
+ * for row i (pna_row_scales),
+ *     y[i, :] = sum_s sum_k  fl(row_scale[i, s] * a[i, k]) * weight[:, s * n_a + k]  + bias,      n_a = n_in / n_scalers
+ * which is the reference's  post_nn[0](cat_s(...))  with every product rounded as the reference rounds it; the scaled
+ * copies exist only in registers.  weight keeps the reference's layout [n_out, n_in = S*A*F] (scaler-major columns).
+ * n_a % 32 == 0, n_out in {64, 128, 256}; workspace as for pna_linear_fwd. */
+int pna_linear_scaled_fwd(const float* a, int64_t lda, const float* row_scale, int32_t n_scalers, const float* weight,
+                          const float* bias, float* y, int64_t ldy, int64_t n_rows, int32_t n_in, int32_t n_out, void* workspace,
+                          size_t workspace_bytes, pna_stream_t stream);
+/* scales[i, s] = factor of scaler s (code (scaler_codes >> 4s) & 15) at in-degree rowptr[i+1] - rowptr[i]; bit-identical
+ * to the factors pna_aggregate_fwd applies (one device function computes both). */
+int pna_row_scales(const int32_t* rowptr, int64_t n_rows, int32_t n_scalers, uint32_t scaler_codes, float avg_log, float avg_lin,
+                   float* scales, pna_stream_t stream);
 
 int pna_query(int what);
 const char* pna_last_error(void);

@@ -27,7 +27,7 @@ BUILD_DIR = os.path.join(_HERE, "csrc", "build")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC"]
 
 # status codes / enums of include/pna_b200.h
-ABI_VERSION = 4
+ABI_VERSION = 5
 PNA_OK = 0
 PNA_F32, PNA_BF16 = 0, 1
 AGGR_CODES = {"sum": 0, "mean": 1, "min": 2, "max": 3, "var": 4, "std": 5, "_skip": 15}
@@ -38,7 +38,7 @@ FLAG_ZERO_ISOLATED, FLAG_SKIP_LIGHT, FLAG_SKIP_HUBS = 1, 2, 4
 
 # every symbol the header declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = ("pna_csr_workspace_bytes", "pna_csr_build", "pna_csr_light_view", "pna_csr_light_view_workspace_bytes", "pna_aggregate_fwd", "pna_aggregate_bwd",
-                    "pna_gather_rows", "pna_linear_fwd", "pna_linear_workspace_bytes", "pna_query", "pna_last_error")
+                    "pna_gather_rows", "pna_linear_fwd", "pna_linear_scaled_fwd", "pna_row_scales", "pna_linear_workspace_bytes", "pna_query", "pna_last_error")
 
 
 class PnaError(RuntimeError):
@@ -166,6 +166,11 @@ def lib() -> C.CDLL:
         L.pna_linear_fwd.restype = C.c_int
         L.pna_linear_fwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                      C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.pna_linear_scaled_fwd.restype = C.c_int
+        L.pna_linear_scaled_fwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.pna_row_scales.restype = C.c_int
+        L.pna_row_scales.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         abi = L.pna_query(QUERY_ABI_VERSION)
         if abi != ABI_VERSION:
             raise ImportError(f"{LIB_PATH} has ABI version {abi}, this package needs {ABI_VERSION}: rebuild it")

@@ -128,6 +128,26 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
     return out
 
 
+def row_scales(csr: CSRGraph, scalers: Names, avg_deg: Mapping[str, float]) -> torch.Tensor:
+    """[N, S] fp32: the factor of every degree scaler for every row (scalers.py:8-29), bit-identical to what the
+    aggregation epilogue multiplies by.  Input of ``pna_linear_scaled_fwd``; cached on the CSR (a graph constant)."""
+    n_scal, codes = _lib.pack_codes(scalers, _lib.SCALER_CODES, "scaler")
+    key = (codes, n_scal, float(avg_deg["log"]), float(avg_deg.get("lin", 1.0)))
+    cache = csr.__dict__.setdefault("_row_scale_cache", {})
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
+    dev = csr.device
+    out = torch.empty((csr.n_nodes, n_scal), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pna_row_scales(_ptr(csr.rowptr), csr.n_nodes, n_scal, codes, key[2], key[3], _ptr(out),
+                                             torch.cuda.current_stream(dev).cuda_stream))
+    if len(cache) > 8:
+        cache.clear()
+    cache[key] = out
+    return out
+
+
 # ---- autograd ----------------------------------------------------------------------------------------------------
 def aggregate_backward(grad_out: torch.Tensor, gathered: torch.Tensor, csr: CSRGraph, aggregators: Names, scalers: Names,
                        avg_deg: Mapping[str, float], *, towers: int = 1, row_bias: Optional[torch.Tensor] = None,

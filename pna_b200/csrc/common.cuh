@@ -51,6 +51,33 @@ struct ViewMap {
   }
 };
 
+// ---- degree scalers (reference models/pytorch_geometric/scalers.py:8-29) --------------------------------------------
+// The ONE place the per-row scale factors are computed: the aggregation epilogue and pna_row_scales (the compact
+// post-linear path) must produce bit-identical factors.
+struct DegScales {
+  float amp, att, lin, ilin;
+  __device__ __forceinline__ float of(unsigned code) const {
+    switch (code) {
+      case PNA_SCALE_IDENTITY: return 1.0f;
+      case PNA_SCALE_AMPLIFICATION: return amp;
+      case PNA_SCALE_ATTENUATION: return att;
+      case PNA_SCALE_LINEAR: return lin;
+      default: return ilin;
+    }
+  }
+};
+__device__ __forceinline__ DegScales deg_scales(int deg, float avg_log, float avg_lin) {
+  const bool iso = deg == 0;
+  const float degf = (float)deg;
+  const float lg = logf(degf + 1.0f);
+  DegScales s;
+  s.amp = __fdiv_rn(lg, avg_log);                      // scalers.py:12-13  (0 for an isolated row)
+  s.att = iso ? 1.0f : __fdiv_rn(avg_log, lg);         // scalers.py:16-19  (scale := 1 where deg == 0)
+  s.lin = __fdiv_rn(degf, avg_lin);                    // scalers.py:22-23
+  s.ilin = iso ? 1.0f : __fdiv_rn(avg_lin, degf);      // scalers.py:26-29
+  return s;
+}
+
 // ---- element load/store with fp32 math -------------------------------------------------------------------
 // Gathered rows go through the read-only path (ld.global.nc); the [N, S*A*F] result is written once and never
 // re-read by this library, so it is stored with the streaming (evict-first) policy to keep source rows in L2.

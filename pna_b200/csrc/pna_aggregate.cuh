@@ -66,6 +66,8 @@ struct CfgStatic {
 // "mean max min std" x "identity amplification attenuation" (realworld_benchmark/configs/*.json) and the
 // "mean min max std" order of models/pytorch_geometric/example.py:33
 using CfgMeanMaxMinStd = CfgStatic<4, (1u) | (3u << 4) | (2u << 8) | (5u << 12), 3, (0u) | (1u << 4) | (2u << 8)>;
+// the same aggregators with the identity scaler only: the compact [N, A*F] tensor of the scaled post-linear path
+using CfgMeanMaxMinStdId = CfgStatic<4, (1u) | (3u << 4) | (2u << 8) | (5u << 12), 1, 0u>;
 using CfgMeanMinMaxStd = CfgStatic<4, (1u) | (2u << 4) | (3u << 8) | (5u << 12), 3, (0u) | (1u << 4) | (2u << 8)>;
 
 // ---- sm_100 packed fp32 arithmetic (FADD2 / FMUL2: two IEEE-rounded fp32 operations per issue slot) and the 3-input
@@ -249,14 +251,7 @@ __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC
   const bool iso = deg == 0;
   const float degf = (float)deg;
   const float cnt = iso ? 1.0f : degf;                     // count.clamp_(1)
-  const float lg = logf(degf + 1.0f);
-  const float s_amp = __fdiv_rn(lg, p.avg_log);            // scalers.py:12-13
-  const float s_att = iso ? 1.0f : __fdiv_rn(p.avg_log, lg);   // scalers.py:16-19
-  float s_lin = 0.f, s_ilin = 0.f;
-  if (!Cfg::kStatic) {
-    s_lin = __fdiv_rn(degf, p.avg_lin);                    // scalers.py:22-23
-    s_ilin = iso ? 1.0f : __fdiv_rn(p.avg_lin, degf);      // scalers.py:26-29
-  }
+  const DegScales ds = deg_scales(deg, p.avg_log, p.avg_lin);   // unused factors are dead code under a static Cfg
   const bool zero_all = iso && (p.flags & PNA_FLAG_ZERO_ISOLATED);
   const int nA = Cfg::kStatic ? Cfg::NA : p.nA, nS = Cfg::kStatic ? Cfg::NS : p.nS;
   const unsigned acodes = Cfg::kStatic ? Cfg::ACODES : p.acodes, scodes = Cfg::kStatic ? Cfg::SCODES : p.scodes;
@@ -304,14 +299,7 @@ __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC
       for (int s = 0; s < Cfg::NS; ++s) {
         if (!Cfg::kStatic && s >= nS) break;
         const unsigned sc = (scodes >> (4 * s)) & 15u;
-        float scale;
-        switch (sc) {
-          case PNA_SCALE_IDENTITY: scale = 1.0f; break;
-          case PNA_SCALE_AMPLIFICATION: scale = s_amp; break;
-          case PNA_SCALE_ATTENUATION: scale = s_att; break;
-          case PNA_SCALE_LINEAR: scale = s_lin; break;
-          default: scale = s_ilin; break;
-        }
+        const float scale = ds.of(sc);
         float o[VEC];
         if constexpr (VEC % 2 == 0) {
 #pragma unroll

@@ -635,7 +635,9 @@ static int launch_config(const KParams& p, cudaStream_t st) {
       PNA_REQUIRE(gx <= 0x7fffffffll, PNA_ERR_UNSUPPORTED, "too many rows for one launch: %lld", slots);
       const unsigned std_s = (0u) | (1u << 4) | (2u << 8);
       const bool s3 = p.nS == 3 && (p.scodes & 0xfffu) == std_s && p.nA == 4;
-      const int cfg = (s3 && (p.acodes & 0xffffu) == CfgMeanMaxMinStd::ACODES) ? 1 : 0;
+      // identity scaler only: the compact [N, A*F] result consumed by pna_linear_scaled_fwd
+      const bool s1 = p.nS == 1 && (p.scodes & 0xfu) == PNA_SCALE_IDENTITY && p.nA == 4;
+      const int cfg = (p.acodes & 0xffffu) != CfgMeanMaxMinStd::ACODES ? 0 : s3 ? 1 : s1 ? 2 : 0;
       if (G == 32 && VEC > 1 && p.lrowptr != nullptr && p.col != nullptr) {
        if constexpr (G == 32 && VEC > 1) {
         // streamed gather over the light view, persistent warps
@@ -665,6 +667,7 @@ static int launch_config(const KParams& p, cudaStream_t st) {
           else PNA_LAUNCH_STREAM(CfgDynamic, true, 2);
         } else if (cfg == 1 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, false, 1);
         else if (cfg == 1) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, true, 1);
+        else if (cfg == 2 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStdId, false, 1);
         else if (!b) PNA_LAUNCH_STREAM(CfgDynamic, false, 1);
         else PNA_LAUNCH_STREAM(CfgDynamic, true, 1);
         chunks_in_stream = p.n_view_rows > p.n_rows;

@@ -15,6 +15,13 @@
 //              (4 K-steps x 3 products); tcgen05.commit releases the stage / signals the epilogue.
 //   warp 9     W producer: the weight is pre-split once per call into the exact swizzled shared-memory image of every
 //              K block, so a W tile is one contiguous cp.async.bulk (TMA 1-D) completing on the stage's mbarrier.
+//
+// Scaled ("compact") mode -- pna_linear_scaled_fwd.  The reference's post-MLP input is cat_s(c_s(i) * agg_i) over the
+// degree scalers s (pna.py:247-249): S copies of the same [N, A*F] aggregate, each multiplied by a per-row factor.  In
+// this mode A is the COMPACT aggregate (identity scaler only) and the loaders regenerate every scaled copy in registers,
+// fl(c_s(i) * a) rounded exactly like the reference's multiply, right before the hi/lo split -- the [N, S*A*F] tensor
+// never exists in HBM: the aggregation writes, and this kernel reads, 1/S of the bytes.  K blocks are visited
+// compact-block-major, scaler-minor; the W tile of step (kb, s) is block s * (K/32) + kb of the reference's weight.
 #include "common.cuh"
 
 namespace pna {
@@ -97,8 +104,9 @@ struct LinSmem {
 // produced once per call by k_split_weight -- so a tile is ONE contiguous bulk copy (TMA 1-D, no tensor map needed).
 template <int O>
 __global__ void __launch_bounds__(kLinThreads, 1)
-k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restrict__ Wimg, const float* __restrict__ bias,
-                float* __restrict__ Y, long long ldy, long long N, int K) {
+k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restrict__ row_scale, int n_rep,
+                const float* __restrict__ Wimg, const float* __restrict__ bias, float* __restrict__ Y, long long ldy, long long N,
+                int K) {
   constexpr int kSt = LinSmem<O>::kSt;
   extern __shared__ unsigned char lin_raw[];
   const unsigned base = (lin_smem_u32(lin_raw) + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
@@ -106,7 +114,8 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
   const unsigned bars = base + kSt * LinSmem<O>::kStage;                    // full[kSt], empty[kSt], tmem_full, tmem slot
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (long long)blockIdx.x * kLinM;
-  const int n_kb = K / kLinBK;
+  const int n_kb = K / kLinBK;          // K blocks of A (compact width)
+  const int n_it = n_kb * n_rep;        // pipeline steps = K blocks of W (n_rep == 1 without row scales)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSt; ++s) {
@@ -145,31 +154,45 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
 #pragma unroll
     for (int u = 0; u < kAhead; ++u) fetch(u, pre[u]);
     unsigned phase = 0;
+    int s = 0;                                              // ring stage of the next pipeline step
     for (int kb0 = 0; kb0 < n_kb; kb0 += kAhead) {
 #pragma unroll
       for (int u = 0; u < kAhead; ++u) {                    // unrolled so that pre[u] stays in registers
         const int kb = kb0 + u;
         if (kb >= n_kb) break;
-        const int s = kb % kSt;
-        lin_mbar_wait(bars + 8 * (kSt + s), phase ^ 1);     // stage free
-        unsigned char* st = gbase + s * LinSmem<O>::kStage;
+        for (int rep = 0; rep < n_rep; ++rep) {             // the scaled copies of this K block (one pass without scales)
+          float sc[kSlabs];
+          if (row_scale) {                                  // issued before the wait: an L1 hit after the first K block
 #pragma unroll
-        for (int sl = 0; sl < kSlabs; ++sl) {
-          const float4 v = pre[u][sl];
-          float4 hi, lo;
-          hi.x = lin_tf32(v.x); lo.x = lin_tf32(v.x - hi.x);
-          hi.y = lin_tf32(v.y); lo.y = lin_tf32(v.y - hi.y);
-          hi.z = lin_tf32(v.z); lo.z = lin_tf32(v.z - hi.z);
-          hi.w = lin_tf32(v.w); lo.w = lin_tf32(v.w - hi.w);
-          const unsigned off = lin_swz(sl * 32 + r_in, j);  // quarter-warps write whole swizzled 128-byte rows: conflict free
-          *reinterpret_cast<float4*>(st + off) = hi;
-          *reinterpret_cast<float4*>(st + LinSmem<O>::kATile + off) = lo;
+            for (int sl = 0; sl < kSlabs; ++sl) {
+              const long long r = row0 + sl * 32 + r_in;
+              sc[sl] = r < N ? __ldg(row_scale + r * n_rep + rep) : 0.f;
+            }
+          }
+          lin_mbar_wait(bars + 8 * (kSt + s), phase ^ 1);   // stage free
+          unsigned char* st = gbase + s * LinSmem<O>::kStage;
+#pragma unroll
+          for (int sl = 0; sl < kSlabs; ++sl) {
+            float4 v = pre[u][sl];
+            if (row_scale) {                                // scalers.py: src * scale, rounded to fp32 like the reference
+              v.x = __fmul_rn(v.x, sc[sl]); v.y = __fmul_rn(v.y, sc[sl]);
+              v.z = __fmul_rn(v.z, sc[sl]); v.w = __fmul_rn(v.w, sc[sl]);
+            }
+            float4 hi, lo;
+            hi.x = lin_tf32(v.x); lo.x = lin_tf32(v.x - hi.x);
+            hi.y = lin_tf32(v.y); lo.y = lin_tf32(v.y - hi.y);
+            hi.z = lin_tf32(v.z); lo.z = lin_tf32(v.z - hi.z);
+            hi.w = lin_tf32(v.w); lo.w = lin_tf32(v.w - hi.w);
+            const unsigned off = lin_swz(sl * 32 + r_in, j);  // quarter-warps write whole swizzled 128-byte rows: conflict free
+            *reinterpret_cast<float4*>(st + off) = hi;
+            *reinterpret_cast<float4*>(st + LinSmem<O>::kATile + off) = lo;
+          }
+          if (rep == n_rep - 1) fetch(kb + kAhead, pre[u]);   // refill the slot just consumed
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to the MMA (async proxy)
+          __syncwarp();
+          if (lane == 0) lin_mbar_arrive(bars + 8 * s);
+          if (++s == kSt) { s = 0; phase ^= 1; }
         }
-        fetch(kb + kAhead, pre[u]);                         // refill the slot just consumed
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to the MMA (async proxy)
-        __syncwarp();
-        if (lane == 0) lin_mbar_arrive(bars + 8 * s);
-        if (s == kSt - 1) phase ^= 1;
       }
     }
     if (warp < 4) {
@@ -189,7 +212,7 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int acc = 1; acc <= LinSmem<O>::kMain; ++acc) {     // the other main accumulator(s) (only if K reached them) + cross terms
-          if (acc < LinSmem<O>::kMain && n_kb <= acc) continue;
+          if (acc < LinSmem<O>::kMain && n_it <= acc) continue;
           unsigned c[16];
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -219,7 +242,7 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
     // ---------------- MMA issuer ----------------
     constexpr unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(O >> 3) << 17) | ((unsigned)(kLinM >> 4) << 24);
     unsigned phase = 0;
-    for (int kb = 0; kb < n_kb; ++kb) {
+    for (int kb = 0; kb < n_it; ++kb) {                     // kb: pipeline step (= K block of the scaled operand)
       const int s = kb % kSt;
       lin_mbar_wait(bars + 8 * s, phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -241,7 +264,7 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
         }
         // release the stage when these MMAs have read it; after the last block also publish the accumulator
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bars + 8 * (kSt + s)) : "memory");
-        if (kb == n_kb - 1)
+        if (kb == n_it - 1)
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bars + 8 * (2 * kSt)) : "memory");
       }
       __syncwarp();
@@ -250,8 +273,9 @@ k_linear_3xtf32(const float* __restrict__ A, long long lda, const float* __restr
   } else if (warp == 9 && lane == 0) {
     // ---------------- W tile producer: two bulk copies (hi, lo images) per K block ----------------
     unsigned phase = 0;
-    for (int kb = 0; kb < n_kb; ++kb) {
-      const int s = kb % kSt;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % kSt;
+      const int kb = (it % n_rep) * n_kb + it / n_rep;     // weight K block of (compact block it / n_rep, scaler it % n_rep)
       lin_mbar_wait(bars + 8 * (kSt + s), phase ^ 1);
       const unsigned st = base + s * LinSmem<O>::kStage + 2 * LinSmem<O>::kATile;
       lin_mbar_expect_tx(bars + 8 * s, 2u * LinSmem<O>::kWTile);
@@ -288,8 +312,8 @@ __global__ void k_split_weight(const float* __restrict__ W, int O, int K, float*
 }
 
 template <int O>
-static int launch_linear(const float* A, long long lda, const float* Wimg, const float* bias, float* Y, long long ldy,
-                         long long N, int K, cudaStream_t st) {
+static int launch_linear(const float* A, long long lda, const float* row_scale, int n_rep, const float* Wimg, const float* bias,
+                         float* Y, long long ldy, long long N, int K, cudaStream_t st) {
   auto kern = k_linear_3xtf32<O>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -297,7 +321,7 @@ static int launch_linear(const float* A, long long lda, const float* Wimg, const
     attr_set = true;
   }
   const long long grid = (N + kLinM - 1) / kLinM;
-  kern<<<(unsigned)grid, kLinThreads, LinSmem<O>::kBytes, st>>>(A, lda, Wimg, bias, Y, ldy, N, K);
+  kern<<<(unsigned)grid, kLinThreads, LinSmem<O>::kBytes, st>>>(A, lda, row_scale, n_rep, Wimg, bias, Y, ldy, N, K);
   PNA_CUDA_TRY(cudaGetLastError());
   return PNA_OK;
 }
@@ -312,25 +336,66 @@ extern "C" int pna_linear_workspace_bytes(int32_t n_in, int32_t n_out, size_t* b
   return PNA_OK;
 }
 
-extern "C" int pna_linear_fwd(const float* a, int64_t lda, const float* weight, const float* bias, float* y, int64_t ldy, int64_t n_rows,
-                              int32_t n_in, int32_t n_out, void* workspace, size_t workspace_bytes, pna_stream_t stream) {
-  PNA_REQUIRE(n_rows >= 0 && n_in > 0 && n_out > 0, PNA_ERR_BAD_ARG, "pna_linear_fwd: bad sizes");
-  PNA_REQUIRE(n_in % kLinBK == 0, PNA_ERR_UNSUPPORTED, "pna_linear_fwd: n_in must be a multiple of %d", kLinBK);
-  PNA_REQUIRE(n_out == 64 || n_out == 128 || n_out == 256, PNA_ERR_UNSUPPORTED, "pna_linear_fwd: n_out must be 64, 128 or 256");
+// a: [n_rows, n_a] (n_a = n_in / n_rep); weight: [n_out, n_in]; row_scale: [n_rows, n_rep] or null (n_rep == 1)
+static int linear_common(const float* a, int64_t lda, const float* row_scale, int32_t n_rep, const float* weight, const float* bias,
+                         float* y, int64_t ldy, int64_t n_rows, int32_t n_in, int32_t n_out, void* workspace, size_t workspace_bytes,
+                         pna_stream_t stream, const char* who) {
+  PNA_REQUIRE(n_rows >= 0 && n_in > 0 && n_out > 0 && n_rep >= 1 && n_rep <= PNA_MAX_SCALERS, PNA_ERR_BAD_ARG, "%s: bad sizes", who);
+  PNA_REQUIRE(n_in % n_rep == 0 && (n_in / n_rep) % kLinBK == 0, PNA_ERR_UNSUPPORTED,
+              "%s: n_in / n_rep must be a multiple of %d", who, kLinBK);
+  PNA_REQUIRE(n_out == 64 || n_out == 128 || n_out == 256, PNA_ERR_UNSUPPORTED, "%s: n_out must be 64, 128 or 256", who);
   if (n_rows == 0) return PNA_OK;
-  PNA_REQUIRE(a && weight && y && workspace, PNA_ERR_BAD_ARG, "pna_linear_fwd: null pointer");
-  PNA_REQUIRE(workspace_bytes >= 2ull * n_in * n_out * sizeof(float), PNA_ERR_WORKSPACE, "pna_linear_fwd: workspace too small");
+  PNA_REQUIRE(a && weight && y && workspace, PNA_ERR_BAD_ARG, "%s: null pointer", who);
+  PNA_REQUIRE(workspace_bytes >= 2ull * n_in * n_out * sizeof(float), PNA_ERR_WORKSPACE, "%s: workspace too small", who);
   PNA_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(workspace) |
                 reinterpret_cast<uintptr_t>(weight)) & 15u) == 0 && lda % 4 == 0 && ldy % 4 == 0,
-              PNA_ERR_UNSUPPORTED, "pna_linear_fwd: a, y, workspace must be 16-byte aligned with pitches that are multiples of 4");
+              PNA_ERR_UNSUPPORTED, "%s: a, y, weight, workspace must be 16-byte aligned with pitches that are multiples of 4", who);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* img = static_cast<float*>(workspace);
   const long long units = (long long)n_out * (n_in / 4);
   k_split_weight<<<(unsigned)((units + 255) / 256), 256, 0, st>>>(weight, n_out, n_in, img);
   PNA_CUDA_TRY(cudaGetLastError());
+  const int n_a = n_in / n_rep;
   switch (n_out) {
-    case 64: return launch_linear<64>(a, lda, img, bias, y, ldy, n_rows, n_in, st);
-    case 128: return launch_linear<128>(a, lda, img, bias, y, ldy, n_rows, n_in, st);
-    default: return launch_linear<256>(a, lda, img, bias, y, ldy, n_rows, n_in, st);
+    case 64: return launch_linear<64>(a, lda, row_scale, n_rep, img, bias, y, ldy, n_rows, n_a, st);
+    case 128: return launch_linear<128>(a, lda, row_scale, n_rep, img, bias, y, ldy, n_rows, n_a, st);
+    default: return launch_linear<256>(a, lda, row_scale, n_rep, img, bias, y, ldy, n_rows, n_a, st);
   }
+}
+
+extern "C" int pna_linear_fwd(const float* a, int64_t lda, const float* weight, const float* bias, float* y, int64_t ldy, int64_t n_rows,
+                              int32_t n_in, int32_t n_out, void* workspace, size_t workspace_bytes, pna_stream_t stream) {
+  return linear_common(a, lda, nullptr, 1, weight, bias, y, ldy, n_rows, n_in, n_out, workspace, workspace_bytes, stream,
+                       "pna_linear_fwd");
+}
+
+extern "C" int pna_linear_scaled_fwd(const float* a, int64_t lda, const float* row_scale, int32_t n_scalers, const float* weight,
+                                     const float* bias, float* y, int64_t ldy, int64_t n_rows, int32_t n_in, int32_t n_out,
+                                     void* workspace, size_t workspace_bytes, pna_stream_t stream) {
+  PNA_REQUIRE(row_scale != nullptr || n_rows == 0, PNA_ERR_BAD_ARG, "pna_linear_scaled_fwd: row_scale is null");
+  return linear_common(a, lda, row_scale, n_scalers, weight, bias, y, ldy, n_rows, n_in, n_out, workspace, workspace_bytes, stream,
+                       "pna_linear_scaled_fwd");
+}
+
+namespace pna {
+__global__ void k_row_scales(const int* __restrict__ rowptr, long long n_rows, int n_scalers, unsigned codes, float avg_log,
+                             float avg_lin, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const DegScales ds = deg_scales(__ldg(rowptr + i + 1) - __ldg(rowptr + i), avg_log, avg_lin);
+  for (int s = 0; s < n_scalers; ++s) out[i * n_scalers + s] = ds.of((codes >> (4 * s)) & 15u);
+}
+}  // namespace pna
+
+extern "C" int pna_row_scales(const int32_t* rowptr, int64_t n_rows, int32_t n_scalers, uint32_t scaler_codes, float avg_log,
+                              float avg_lin, float* scales, pna_stream_t stream) {
+  PNA_REQUIRE(n_rows >= 0 && n_scalers >= 1 && n_scalers <= PNA_MAX_SCALERS, PNA_ERR_BAD_ARG, "pna_row_scales: bad sizes");
+  for (int s = 0; s < n_scalers; ++s)
+    PNA_REQUIRE(((scaler_codes >> (4 * s)) & 15u) <= PNA_SCALE_INVERSE_LINEAR, PNA_ERR_BAD_ARG, "pna_row_scales: bad scaler code");
+  if (n_rows == 0) return PNA_OK;
+  PNA_REQUIRE(rowptr && scales, PNA_ERR_BAD_ARG, "pna_row_scales: null pointer");
+  k_row_scales<<<(unsigned)((n_rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, n_rows, n_scalers, scaler_codes,
+                                                                                            avg_log, avg_lin, scales);
+  PNA_CUDA_TRY(cudaGetLastError());
+  return PNA_OK;
 }

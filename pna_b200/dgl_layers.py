@@ -13,7 +13,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import padding as pad
-from .aggregate import pna_aggregate
+from .aggregate import pna_aggregate, row_scales
+from .linear import scaled_kernel_applies
 from .graph import graph_csr
 from .nn_blocks import FCLayer, MLP
 
@@ -167,13 +168,18 @@ class PNASimpleLayer(nn.Module):
     def forward(self, g, h):
         h_in = h
         fp = pad.padded_width(self.in_dim, h.dtype)
-        if fp == self.in_dim:
-            h = self.posttrans(self.aggregate_only(g, h))
-        else:   # odd width: 128-bit path on zero-padded rows, padding absorbed by the first posttrans Linear
-            agg = pna_aggregate(pad.pad_cols(h, fp), graph_csr(g, h.device), self.aggregators, self.scalers, self.avg_d,
-                                zero_isolated=True)
-            blocks = len(self.aggregators) * len(self.scalers)
-            w0 = pad.expand_weight_cols(self.posttrans.fully_connected[0].linear.weight, blocks, self.in_dim, fp)
+        csr = graph_csr(g, h.device)
+        blocks = len(self.aggregators) * len(self.scalers)
+        w0 = self.posttrans.fully_connected[0].linear.weight
+        if fp != self.in_dim:   # odd width: 128-bit path on zero-padded rows, padding absorbed by the first posttrans Linear
+            w0 = pad.expand_weight_cols(w0, blocks, self.in_dim, fp)
+        hp = pad.pad_cols(h, fp)
+        if h.size(0) > 0 and scaled_kernel_applies(h.new_empty((1, len(self.aggregators) * fp)), w0, len(self.scalers)):
+            # compact post path: identity-scaled aggregate, the scaled copies are formed inside the tensor-core linear
+            agg = pna_aggregate(hp, csr, self.aggregators, ["identity"], self.avg_d, zero_isolated=True)
+            h = self.posttrans(agg, first_weight=w0, first_row_scale=row_scales(csr, self.scalers, self.avg_d))
+        else:
+            agg = pna_aggregate(hp, csr, self.aggregators, self.scalers, self.avg_d, zero_isolated=True)
             h = self.posttrans(agg, first_weight=w0)
         if self.batch_norm:
             h = self.batchnorm_h(h)

@@ -317,7 +317,7 @@ def bench_multi_gpu(args, metric, unit, aggrs, scalers, measured_peaks, ClockSam
         blk = (n_local + 7) // 8
         with torch.no_grad():
             for r0 in range(0, n_local, blk):      # post-MLP in row blocks, each copied back while the next is computed
-                y = lay._post(a[r0:r0 + blk], a.dtype)          # first Linear on the tensor cores (pna_linear_fwd)
+                y = lay._post(a[r0:r0 + blk], None, a.dtype)         # first Linear on the tensor cores (pna_linear_fwd)
                 s_out.wait_stream(main)
                 with torch.cuda.stream(s_out):
                     outh[r0:r0 + blk].copy_(y, non_blocking=True)

@@ -46,9 +46,13 @@ class FCLayer(nn.Module):
         if self.bias:
             self.linear.bias.data.zero_()
 
-    def forward(self, x, weight=None):
-        """`weight`: optional replacement for linear.weight (same parameters, zero columns inserted for padded inputs)."""
-        if x.dim() == 2:   # tensor-core path for the shapes pna_linear_fwd takes, library GEMM otherwise
+    def forward(self, x, weight=None, row_scale=None):
+        """`weight`: optional replacement for linear.weight (same parameters, zero columns inserted for padded inputs).
+        `row_scale` [N, S]: x is the compact aggregate and the S scaled copies are formed inside the kernel (linear.py)."""
+        if row_scale is not None:
+            from .linear import post_linear_scaled
+            h = post_linear_scaled(x, row_scale, self.linear.weight if weight is None else weight, self.linear.bias)
+        elif x.dim() == 2:   # tensor-core path for the shapes pna_linear_fwd takes, library GEMM otherwise
             from .linear import post_linear
             h = post_linear(x, self.linear.weight if weight is None else weight, self.linear.bias)
         else:
@@ -79,9 +83,9 @@ class MLP(nn.Module):
             self.fully_connected.append(FCLayer(sizes[k], sizes[k + 1], activation=last_activation if last else mid_activation,
                                                 b_norm=last_b_norm if last else mid_b_norm, device=device, dropout=dropout))
 
-    def forward(self, x, first_weight=None):
+    def forward(self, x, first_weight=None, first_row_scale=None):
         for k, fc in enumerate(self.fully_connected):
-            x = fc(x, first_weight) if (k == 0 and first_weight is not None) else fc(x)
+            x = fc(x, first_weight, first_row_scale) if k == 0 else fc(x)
         return x
 
     def is_single_affine(self) -> bool:

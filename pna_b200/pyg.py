@@ -14,8 +14,8 @@ from torch import Tensor
 from torch.nn import Linear, Module, ModuleList, ReLU, Sequential
 
 from . import padding as pad
-from .aggregate import avg_deg_from_histogram, pna_aggregate
-from .linear import post_linear
+from .aggregate import avg_deg_from_histogram, pna_aggregate, row_scales
+from .linear import post_linear, post_linear_scaled, scaled_kernel_applies
 from .csr import CSRGraph, csr_from_edge_index
 
 _AGGRS = ("sum", "mean", "min", "max", "var", "std")          # aggregators.py:35-42
@@ -80,20 +80,38 @@ class PNAConvSimple(Module):
                 deg: Optional[Tensor] = None, csr: Optional[CSRGraph] = None) -> Tensor:
         # `deg` (precomputed in-degree) is accepted for signature compatibility with BASELINE.json's wording; the
         # in-degree always comes from the CSR row pointer, which is what degree(index) recounts in pna.py:247.
-        return self._post(self._aggregate_padded(x, _resolve_csr(x, edge_index, csr)), x.dtype)
+        agg, rs = self._aggregate_padded(x, _resolve_csr(x, edge_index, csr))
+        return self._post(agg, rs, x.dtype)
 
-    def _aggregate_padded(self, x: Tensor, csr: CSRGraph) -> Tensor:
-        """Aggregation at the kernel's 16-byte feature granularity: odd widths (e.g. 75) run on zero-padded rows."""
-        Fp = pad.padded_width(self.F_in, x.dtype)
-        return pna_aggregate(pad.pad_cols(x, Fp), csr, self.aggregators, self.scalers, self.avg_deg)
-
-    def _post(self, agg: Tensor, dtype) -> Tensor:
-        """post_nn on (a row block of) the aggregated tensor; padding is absorbed by zero columns of the first Linear."""
+    def _first_weight(self, dtype) -> Tensor:
+        """weight of post_nn[0] at the padded feature width (zero columns at the pad positions)."""
         Fp = pad.padded_width(self.F_in, dtype)
-        blocks = len(self.aggregators) * len(self.scalers)
+        return pad.expand_weight_cols(self.post_nn[0].weight, len(self.aggregators) * len(self.scalers), self.F_in, Fp)
+
+    def _compact(self, x: Tensor) -> bool:
+        """Compact post path: aggregate with the identity scaler only ([N, A*F]) and let the tensor-core
+        linear regenerate the scaled copies in registers -- the [N, S*A*F] tensor is never written.  Same arithmetic."""
+        Fp = pad.padded_width(self.F_in, x.dtype)
+        probe = x.new_empty((1, len(self.aggregators) * Fp))          # shape/dtype/device stand-in for the aggregate
+        return x.size(0) > 0 and scaled_kernel_applies(probe, self._first_weight(x.dtype), len(self.scalers))
+
+    def _aggregate_padded(self, x: Tensor, csr: CSRGraph):
+        """Aggregation at the kernel's 16-byte feature granularity: odd widths (e.g. 75) run on zero-padded rows.
+        Returns (aggregate, row_scale): row_scale is None for the full [N, S*A*F] tensor, [N, S] for the compact one."""
+        Fp = pad.padded_width(self.F_in, x.dtype)
+        if self._compact(x):
+            return (pna_aggregate(pad.pad_cols(x, Fp), csr, self.aggregators, ["identity"], self.avg_deg),
+                    row_scales(csr, self.scalers, self.avg_deg))
+        return pna_aggregate(pad.pad_cols(x, Fp), csr, self.aggregators, self.scalers, self.avg_deg), None
+
+    def _post(self, agg: Tensor, row_scale: Optional[Tensor], dtype) -> Tensor:
+        """post_nn on (a row block of) the aggregated tensor; padding is absorbed by zero columns of the first Linear."""
         lin0 = self.post_nn[0]
         # first Linear: tensor cores (3xTF32 tcgen05, pna_linear_fwd) when the shape allows, else the library GEMM
-        out = post_linear(agg, pad.expand_weight_cols(lin0.weight, blocks, self.F_in, Fp), lin0.bias)
+        if row_scale is not None:
+            out = post_linear_scaled(agg, row_scale, self._first_weight(dtype), lin0.bias)
+        else:
+            out = post_linear(agg, self._first_weight(dtype), lin0.bias)
         for m in list(self.post_nn)[1:]:
             out = m(out)
         return out
@@ -120,12 +138,12 @@ class PNAConvSimple(Module):
         csr = csr_from_edge_index(ei_d, n)                      # radix sort + views while x is on the wire
         main.wait_stream(s_in)
         x_d.record_stream(main)
-        agg = self._aggregate_padded(x_d, csr)
+        agg, rs = self._aggregate_padded(x_d, csr)
         if out is None:
             out = torch.empty((n, self.F_out), dtype=x.dtype, pin_memory=True)
         step = max(1, (n + row_blocks - 1) // row_blocks)
         for r0 in range(0, n, step):
-            y = self._post(agg[r0:r0 + step], x.dtype)
+            y = self._post(agg[r0:r0 + step], None if rs is None else rs[r0:r0 + step], x.dtype)
             s_out.wait_stream(main)
             with torch.cuda.stream(s_out):
                 out[r0:r0 + step].copy_(y, non_blocking=True)
