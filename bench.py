@@ -243,7 +243,9 @@ def run_ours(args):
     clocks = clk.summary()
     t_ms = sum(per_step) / len(per_step)
     value = e / (t_ms * 1e-3)
-    launches_per_step = 1 + (1 if csr.n_hubs else 0)       # k_rows_stream (+ k_hub_finalize when rows were split)
+    from pna_b200.aggregate import fold_finalize_enabled
+    # k_rows_stream (+ k_hub_finalize when rows were split and the finalize is not folded into the stream kernel)
+    launches_per_step = 1 + (1 if (csr.n_hubs and not fold_finalize_enabled()) else 0)
     # (the e2e / layer_fwd legs additionally launch k_split_weight + k_linear_3xtf32 and the CSR-build kernels)
 
     bytes_ = synth.algorithmic_bytes(n, e, f, 4, 12 * f)
@@ -331,7 +333,9 @@ def run_ours(args):
                      "b_min_bytes": bytes_["b_min"], "b_gather_bytes": bytes_["b_gather"],
                      "effective_gbs_b_gather": bytes_["b_gather"] / (t_ms * 1e-3) / 1e9},
         "kernels_ms": {"step_min": min(per_step), "step_median": statistics.median(per_step),
-                       "kernels": "k_rows_stream (rows + chunks of split rows) + k_hub_finalize; per-kernel times: profiles/"},
+                       "kernels": ("k_rows_stream (rows + chunks of split rows, split rows finalized by the last-arriving warp)"
+                                   if fold_finalize_enabled() else "k_rows_stream (rows + chunks of split rows) + k_hub_finalize")
+                                  + "; per-kernel times: profiles/"},
         "layer_fwd": {"ms": full_ms, "edges_per_s": e / (full_ms * 1e-3), "ms_via_12f_tensor": full_ms_12f,
                       "what": "PNAConvSimple.forward, CSR cached: aggregation with the identity scaler ([N,4F]) + post-MLP linear on "
                               "the tensor cores regenerating the scaled copies in registers (pna_linear_scaled_fwd, 3xTF32 "

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNA_ABI_VERSION 5
+#define PNA_ABI_VERSION 6
 
 typedef void* pna_stream_t; /* a cudaStream_t / CUstream, passed opaquely */
 
@@ -199,6 +199,11 @@ typedef struct pna_agg {
   const void* const* peer_gathered;
   int32_t peer_shift;
   int32_t reserved;
+  /* optional int32 [9 * n_hubs] completion counters, ZERO before the first call (the library leaves them zero): when
+   * given together with a view that contains the chunk pseudo-rows, the warp that stores the last partial of a split row
+   * also merges and finalizes it (same merge order as the separate finalize kernel), so a layer call is ONE launch with
+   * no serial tail.  NULL: split rows are finalized by a second small kernel.  Not to be shared by concurrent calls. */
+  int32_t* hub_done;
 } pna_agg_t;
 
 int pna_aggregate_fwd(const pna_agg_t* desc, pna_stream_t stream);

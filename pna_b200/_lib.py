@@ -27,7 +27,7 @@ BUILD_DIR = os.path.join(_HERE, "csrc", "build")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC"]
 
 # status codes / enums of include/pna_b200.h
-ABI_VERSION = 5
+ABI_VERSION = 6
 PNA_OK = 0
 PNA_F32, PNA_BF16 = 0, 1
 AGGR_CODES = {"sum": 0, "mean": 1, "min": 2, "max": 3, "var": 4, "std": 5, "_skip": 15}
@@ -83,7 +83,7 @@ class AggStruct(C.Structure):
         ("row_ids", C.c_void_p), ("n_row_ids", C.c_int64),
         ("light_rowptr", C.c_void_p), ("light_deg", C.c_void_p), ("light_col", C.c_void_p), ("part", C.c_void_p),
         ("n_part", C.c_int32), ("n_view_rows", C.c_int64), ("peer_gathered", C.c_void_p), ("peer_shift", C.c_int32),
-        ("reserved", C.c_int32),
+        ("reserved", C.c_int32), ("hub_done", C.c_void_p),
     ]
 
 

@@ -7,6 +7,7 @@ E x F message tensor (aggregators.py:9-32), three scaler passes (scalers.py:8-19
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Mapping, Optional, Sequence, Union
 
 import torch
@@ -34,6 +35,11 @@ def _rows2d(t: torch.Tensor, what: str) -> torch.Tensor:
     if t.size(0) > 1 and t.stride(0) < t.size(1):
         t = t.contiguous()
     return t
+
+
+def fold_finalize_enabled() -> bool:
+    """PNA_B200_FOLD_FINALIZE=1: the warp that completes a split row also finalizes it (one launch per call)."""
+    return os.environ.get("PNA_B200_FOLD_FINALIZE", "0") == "1"
 
 
 def output_width(n_feat: int, n_aggr: int, n_scalers: int, has_self: bool) -> int:
@@ -111,6 +117,8 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
         row_ids=_ptr(row_ids), n_row_ids=0 if row_ids is None else int(row_ids.numel()))
     if view is None and row_ids is None:
         view = csr.full_view()
+        if fold_finalize_enabled() and not skip_hubs and peer is None:
+            d.hub_done = _ptr(csr.hub_done())      # split rows finalized inside the same launch
     if view is not None and row_ids is None and N > 0:
         # light view (whole graph: built with the CSR; row subset: CSRGraph.masked_view) -> streamed-gather kernel
         d.light_rowptr, d.light_deg, d.part, d.n_part = _ptr(view.light_rowptr), _ptr(view.light_deg), _ptr(view.part), view.n_part

@@ -83,6 +83,17 @@ class CSRGraph:
             self._partials[n_feat] = buf
         return buf
 
+    def hub_done(self) -> Optional[torch.Tensor]:
+        """int32 [9 * n_hubs] completion counters of the folded finalize (pna_agg_t.hub_done): zero-initialised once,
+        left zero by every call.  One set per CSR: calls that share a CSR must be stream-ordered (as for hub_partials)."""
+        if self.n_hubs == 0:
+            return None
+        buf = self._partials.get("done")
+        if buf is None:
+            buf = torch.zeros(9 * self.n_hubs, dtype=torch.int32, device=self.device)
+            self._partials["done"] = buf
+        return buf
+
     def masked_view(self, row_mask: torch.Tensor) -> LightView:
         """Light view of the rows with ``row_mask != 0`` only (uint8/bool [N]); other rows are skipped by the kernel."""
         N, dev = self.n_nodes, self.device

@@ -52,6 +52,7 @@ extern "C" int pna_aggregate_fwd(const pna_agg_t* d, pna_stream_t stream) {
   p.flags = d->flags; p.split = d->split_threshold; p.chunk = d->chunk_edges;
   p.hub_info = d->hub_info; p.chunk_items = d->chunk_items; p.n_hubs = d->n_hubs; p.n_chunks = d->n_chunks;
   p.partials = d->hub_partials;
+  p.hub_done = d->hub_done;
   p.row_ids = d->row_ids; p.n_row_ids = d->row_ids ? d->n_row_ids : 0;
   // a view that contains chunk pseudo-rows cannot be used when the split rows are to be skipped
   const bool view = d->light_rowptr && d->light_deg && d->part && d->n_part >= 1 && (d->light_col || !d->col) &&

@@ -32,6 +32,7 @@ struct KParams {
   int split, chunk;
   const int* hub_info; const int* chunk_items; long long n_hubs, n_chunks;
   float* partials;
+  int* hub_done;           // nullable: per split row 8 group counters + 1 row counter (finalize folded into the stream kernel)
   const int* row_ids; long long n_row_ids;
   const int* lrowptr; const int* ldeg; const int* lcol; const int* part; int n_part;   // light view (nullable)
   long long n_view_rows;   // > n_rows: view rows n_rows + c are chunk pseudo-rows reduced into partials[c]

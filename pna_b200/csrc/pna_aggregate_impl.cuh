@@ -297,8 +297,119 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
 #define PNA_STREAM_TMA 0   // 1: per-row cp.async.bulk (UBLKCP) + mbarrier; 0: per-lane 16-byte cp.async (LDGSTS) groups
 #endif
 
-template <typename T, int VEC, int K, typename Cfg, bool BIAS, int DEPTH>
-__global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_rows_stream(const KParams p) {
+// ---- hubs, pass 2: one CTA per hub merges its partials, then the common epilogue ---------------------------
+// kFinGroups lane groups stride over the hub's chunks (group q takes chunks q, q+kFinGroups, ..), each merging in
+// chunk order; the per-group results are parked in the groups' own first partial slots (scratch, rebuilt every call)
+// and group 0 merges those in group order.  Deterministic; no atomics; a 20k-edge hub is ~20 chunk reads per group.
+constexpr int kFinGroups = 8;
+
+template <int VEC, int K, int UF>
+__device__ __forceinline__ void merge_partials(const float* __restrict__ base, long long F, const int (&f)[K], const bool (&ok)[K],
+                                               int first, int count, int stride, Acc<VEC> (&acc)[K]) {
+  for (int j = 0; j < count; j += UF) {
+    float ps[UF][K][4][VEC];
+#pragma unroll
+    for (int u = 0; u < UF; ++u) {
+      if (j + u < count) {
+        const float* part = base + (long long)(first + (long long)(j + u) * stride) * 4ll * F;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (ok[k]) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              // L2 loads (ld.global.cg): written earlier on this stream, by this CTA, or -- folded finalize -- by a warp of
+              // another SM in the same launch, ordered by __threadfence + the completion counter
+              const float* src = part + (long long)q * F + f[k];
+              if constexpr (VEC % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < VEC; i += 4) {
+                  const float4 t = __ldcg(reinterpret_cast<const float4*>(src + i));
+                  ps[u][k][q][i] = t.x; ps[u][k][q][i + 1] = t.y; ps[u][k][q][i + 2] = t.z; ps[u][k][q][i + 3] = t.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) ps[u][k][q][i] = __ldcg(src + i);
+              }
+            }
+          }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UF; ++u) {
+      if (j + u < count) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (ok[k]) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              acc[k].sum[i] = __fadd_rn(acc[k].sum[i], ps[u][k][0][i]);
+              acc[k].sq[i] = __fadd_rn(acc[k].sq[i], ps[u][k][1][i]);
+              acc[k].mn[i] = fminf(acc[k].mn[i], ps[u][k][2][i]);
+              acc[k].mx[i] = fmaxf(acc[k].mx[i], ps[u][k][3][i]);
+            }
+          }
+      }
+    }
+  }
+}
+
+// ---- folded finalize of the split rows (pna_agg_t.hub_done): completion counters instead of a second kernel ------------
+// Called by the warp that has just stored the partial of chunk c.  The warp that completes the last chunk of merge
+// group g (chunks g, g+8, .. of the split row) merges that group in chunk order and parks the result in the group's first
+// slot; the warp that completes the last group merges the 8 group results in order and runs the row epilogue -- the same
+// two-level order as k_hub_finalize, hence the same bits, deterministic.  Nobody waits: whoever arrives last does the
+// work.  Counters are reset by their last visitor.  Out of line so that the streaming loop keeps its registers.
+template <typename T, int VEC, int K, typename Cfg>
+__device__ __noinline__ void fold_split_row(const KParams& p, int c, int fblock) {
+  constexpr int G = 32;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int UFm = (K * VEC >= 8) ? 1 : 2;
+  const int lane = threadIdx.x & 31;
+  FeatMap<VEC, G, K> fm;
+  fm.init(p, lane, fblock);
+  Acc<VEC> acc[K];
+  const int h = __ldg(p.chunk_items + 2 * c), jc = __ldg(p.chunk_items + 2 * c + 1);
+  const int first = __ldg(p.hub_info + 4 * h + 1), nch = __ldg(p.hub_info + 4 * h + 2);
+  int* cnt = p.hub_done + 9ll * h;
+  auto arrive = [&](int* ctr) -> int {   // publishes this warp's stored partial, returns the arrival index
+    __threadfence();
+    __syncwarp();
+    int t = 0;
+    if (lane == 0) t = atomicAdd(ctr, 1);
+    return __shfl_sync(FULL, t, 0);
+  };
+  if (nch > kFinGroups) {
+    const int g = jc % kFinGroups;
+    const int mine = (nch - g + kFinGroups - 1) / kFinGroups;
+    if (arrive(cnt + g) != mine - 1) return;
+    if (lane == 0) cnt[g] = 0;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k].init();
+    merge_partials<VEC, K, UFm>(p.partials, p.F, fm.f, fm.ok, first + g, mine, kFinGroups, acc);
+    float* __restrict__ part = p.partials + (long long)(first + g) * 4ll * p.F;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (!fm.ok[k]) continue;
+      store_f32<VEC>(part + 0ll * p.F + fm.f[k], acc[k].sum);
+      store_f32<VEC>(part + 1ll * p.F + fm.f[k], acc[k].sq);
+      store_f32<VEC>(part + 2ll * p.F + fm.f[k], acc[k].mn);
+      store_f32<VEC>(part + 3ll * p.F + fm.f[k], acc[k].mx);
+    }
+    if (arrive(cnt + 8) != kFinGroups - 1) return;
+  } else if (arrive(cnt + 8) != nch - 1) {
+    return;
+  }
+  if (lane == 0) cnt[8] = 0;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k].init();
+  merge_partials<VEC, K, UFm>(p.partials, p.F, fm.f, fm.ok, first, nch > kFinGroups ? kFinGroups : nch, 1, acc);
+  finalize_row<T, VEC, G, K, Cfg>(p, fm, (long long)__ldg(p.hub_info + 4 * h), __ldg(p.hub_info + 4 * h + 3), acc);
+}
+
+template <typename T, int VEC, int K, typename Cfg, bool BIAS, int DEPTH, bool FOLD = false>
+__global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_rows_stream(const __grid_constant__ KParams p) {
   constexpr int G = 32;
   constexpr int H = StreamGeom<T, VEC, K, DEPTH>::kH;
   constexpr int SLOT = StreamGeom<T, VEC, K, DEPTH>::kBlockBytes;
@@ -484,6 +595,8 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
           store_f32<VEC>(part + 2ll * p.F + fm.f[k], acc[k].mn);
           store_f32<VEC>(part + 3ll * p.F + fm.f[k], acc[k].mx);
         }
+        // FOLD is a separate instantiation: the out-of-line call costs the streaming loop registers (ABI partition)
+        if constexpr (FOLD) fold_split_row<T, VEC, K, Cfg>(p, row - (int)p.n_rows, fblock);
       }
     }
     dg = dgN; rid = ridN;
@@ -526,60 +639,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks(VEC, K)) k_hub_chunks(con
   }
 }
 
-// ---- hubs, pass 2: one CTA per hub merges its partials, then the common epilogue ---------------------------
-// kFinGroups lane groups stride over the hub's chunks (group q takes chunks q, q+kFinGroups, ..), each merging in
-// chunk order; the per-group results are parked in the groups' own first partial slots (scratch, rebuilt every call)
-// and group 0 merges those in group order.  Deterministic; no atomics; a 20k-edge hub is ~20 chunk reads per group.
-constexpr int kFinGroups = 8;
-
-template <int VEC, int K, int UF>
-__device__ __forceinline__ void merge_partials(const float* __restrict__ base, long long F, const int (&f)[K], const bool (&ok)[K],
-                                               int first, int count, int stride, Acc<VEC> (&acc)[K]) {
-  for (int j = 0; j < count; j += UF) {
-    float ps[UF][K][4][VEC];
-#pragma unroll
-    for (int u = 0; u < UF; ++u) {
-      if (j + u < count) {
-        const float* part = base + (long long)(first + (long long)(j + u) * stride) * 4ll * F;
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-          if (ok[k]) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float* src = part + (long long)q * F + f[k];   // plain loads: written earlier on this stream / CTA
-              if constexpr (VEC % 4 == 0) {
-#pragma unroll
-                for (int i = 0; i < VEC; i += 4) {
-                  const float4 t = *reinterpret_cast<const float4*>(src + i);
-                  ps[u][k][q][i] = t.x; ps[u][k][q][i + 1] = t.y; ps[u][k][q][i + 2] = t.z; ps[u][k][q][i + 3] = t.w;
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) ps[u][k][q][i] = src[i];
-              }
-            }
-          }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UF; ++u) {
-      if (j + u < count) {
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-          if (ok[k]) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-              acc[k].sum[i] = __fadd_rn(acc[k].sum[i], ps[u][k][0][i]);
-              acc[k].sq[i] = __fadd_rn(acc[k].sq[i], ps[u][k][1][i]);
-              acc[k].mn[i] = fminf(acc[k].mn[i], ps[u][k][2][i]);
-              acc[k].mx[i] = fmaxf(acc[k].mx[i], ps[u][k][3][i]);
-            }
-          }
-      }
-    }
-  }
-}
-
+// ---- hubs, pass 2 (k_hub_finalize): merge_partials / kFinGroups are defined above k_rows_stream ------------------------
 template <typename T, int VEC, int G, int K>
 __global__ void __launch_bounds__(kFinGroups * 32) k_hub_finalize(const KParams p) {
   constexpr int UF = (K * VEC >= 16) ? 1 : (K * VEC >= 8 ? 2 : 4);  // partial sets in flight (register budget)
@@ -623,10 +683,14 @@ __global__ void __launch_bounds__(kFinGroups * 32) k_hub_finalize(const KParams 
 
 // ---- host dispatch -----------------------------------------------------------------------------------------
 template <typename T, int VEC, int G, int K, int U>
-static int launch_config(const KParams& p, cudaStream_t st) {
+static int launch_config(const KParams& p_in, cudaStream_t st) {
   constexpr int RPW = 32 / G;
   constexpr int per_block = (kThreads / 32) * RPW;
+  KParams p = p_in;
   const unsigned gy = (unsigned)((p.F + G * VEC * K - 1) / (G * VEC * K));
+  // folded finalize: one counter set per split row, i.e. one feature block, and only the streamed kernel implements it
+  if (gy != 1 || !(p.n_view_rows > p.n_rows)) p.hub_done = nullptr;
+  bool folded = false;
   bool chunks_in_stream = false;   // the streamed kernel also reduced the chunks of the split rows
   if (!(p.flags & PNA_FLAG_SKIP_LIGHT)) {
     const long long slots = p.row_ids ? p.n_row_ids : p.n_rows;
@@ -643,10 +707,10 @@ static int launch_config(const KParams& p, cudaStream_t st) {
         // streamed gather over the light view, persistent warps
         const bool b = p.bias != nullptr;
         const bool deep = p.peer_x != nullptr;
-#define PNA_LAUNCH_STREAM(CFG, B, DEPTH)                                                                           \
+#define PNA_LAUNCH_STREAM_(CFG, B, DEPTH, FOLD)                                                                         \
   do {                                                                                                             \
     constexpr size_t smem = StreamGeom<T, VEC, K, DEPTH>::kSmem;                                                   \
-    auto kern = k_rows_stream<T, VEC, K, CFG, B, DEPTH>;                                                           \
+    auto kern = k_rows_stream<T, VEC, K, CFG, B, DEPTH, FOLD>;                                                         \
     static int resident = 0;  /* CTAs of this kernel that fit the device (all B200s alike) */                     \
     if (resident == 0) {                                                                                           \
       if (smem > 48 * 1024) PNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -661,17 +725,26 @@ static int launch_config(const KParams& p, cudaStream_t st) {
     if (gxs < 1) gxs = 1;                                                                                          \
     kern<<<dim3((unsigned)gxs, gy), kStreamThreads, smem, st>>>(p);                                                \
   } while (0)
+        // single-GPU kernels exist with and without the folded finalize; the peer (DEPTH 2) kernels without
+#define PNA_LAUNCH_STREAM(CFG, B)                                        \
+  do {                                                                   \
+    if (p.hub_done) PNA_LAUNCH_STREAM_(CFG, B, 1, true);                 \
+    else PNA_LAUNCH_STREAM_(CFG, B, 1, false);                           \
+  } while (0)
         if (deep) {
-          if (cfg == 1 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, false, 2);
-          else if (!b) PNA_LAUNCH_STREAM(CfgDynamic, false, 2);
-          else PNA_LAUNCH_STREAM(CfgDynamic, true, 2);
-        } else if (cfg == 1 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, false, 1);
-        else if (cfg == 1) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, true, 1);
-        else if (cfg == 2 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStdId, false, 1);
-        else if (!b) PNA_LAUNCH_STREAM(CfgDynamic, false, 1);
-        else PNA_LAUNCH_STREAM(CfgDynamic, true, 1);
+          p.hub_done = nullptr;
+          if (cfg == 1 && !b) PNA_LAUNCH_STREAM_(CfgMeanMaxMinStd, false, 2, false);
+          else if (!b) PNA_LAUNCH_STREAM_(CfgDynamic, false, 2, false);
+          else PNA_LAUNCH_STREAM_(CfgDynamic, true, 2, false);
+        } else if (cfg == 1 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, false);
+        else if (cfg == 1) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, true);
+        else if (cfg == 2 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStdId, false);
+        else if (!b) PNA_LAUNCH_STREAM(CfgDynamic, false);
+        else PNA_LAUNCH_STREAM(CfgDynamic, true);
         chunks_in_stream = p.n_view_rows > p.n_rows;
+        folded = chunks_in_stream && p.hub_done != nullptr;
 #undef PNA_LAUNCH_STREAM
+#undef PNA_LAUNCH_STREAM_
        }
       } else if constexpr (G >= U && G % U == 0) {
         constexpr int TR = (8 * RPW < 32) ? 8 * RPW : 32;
@@ -697,8 +770,10 @@ static int launch_config(const KParams& p, cudaStream_t st) {
       k_hub_chunks<T, VEC, G, K, U><<<dim3((unsigned)gc, gy), kThreads, 0, st>>>(p);
       PNA_CUDA_TRY(cudaGetLastError());
     }
-    k_hub_finalize<T, VEC, G, K><<<dim3((unsigned)p.n_hubs, gy), kFinGroups * G, 0, st>>>(p);
-    PNA_CUDA_TRY(cudaGetLastError());
+    if (!folded) {
+      k_hub_finalize<T, VEC, G, K><<<dim3((unsigned)p.n_hubs, gy), kFinGroups * G, 0, st>>>(p);
+      PNA_CUDA_TRY(cudaGetLastError());
+    }
   }
   return PNA_OK;
 }

@@ -768,3 +768,66 @@ def test_compact_layers_match_the_uncompacted_path(P, O, monkeypatch):
         monkeypatch.setenv("PNA_B200_COMPACT_POST", "0")
         b = dl(gr, xd)
     torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5)
+
+
+# ---- folded finalize of the split rows (pna_agg_t.hub_done) ----------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_folded_finalize_is_bit_identical_and_reusable(P, O, monkeypatch, dtype):
+    """One launch instead of two: the warp completing a split row finalizes it.  Same merge order => same bits as the
+    separate finalize kernel; counters return to zero so that the next call (same CSR) works."""
+    n, f = 6000, 128
+    g = torch.Generator().manual_seed(31)
+    ei = rand_graph(n, 30000, 32, hub=5000)                        # one row with ~5000 in-edges: 40 chunks, two-level
+    extra_dst = torch.cat([torch.full((300,), 7), torch.full((900,), 8), torch.full((1100,), 9)])   # 3, 8 and 9 chunks
+    extra = torch.stack([torch.randint(0, n, (extra_dst.numel(),), generator=g), extra_dst])
+    ei = torch.cat([ei, extra], dim=1)
+    x = torch.randn(n, f, generator=g).to(dtype).to(dev())
+    u = torch.randn(n, f, generator=g).to(dtype).to(dev())
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n)
+    assert csr.n_hubs >= 4
+    avg = avg_deg_of(ei, n, O)
+    cases = [dict(aggregators=A4, scalers=S3), dict(aggregators=A4, scalers=["identity"]),
+             dict(aggregators=["sum", "var", "max"], scalers=["linear", "attenuation"]),
+             dict(aggregators=A4, scalers=S3, row_bias=u), dict(aggregators=A4, scalers=S3, zero_isolated=True)]
+    for kw in cases:
+        a, s = kw.pop("aggregators"), kw.pop("scalers")
+        monkeypatch.setenv("PNA_B200_FOLD_FINALIZE", "0")
+        want = P.aggregate_forward(x, csr, a, s, avg, **kw)
+        monkeypatch.setenv("PNA_B200_FOLD_FINALIZE", "1")
+        for _ in range(3):                                          # counters are reset by the kernel itself
+            got = P.aggregate_forward(x, csr, a, s, avg, **kw)
+            assert torch.equal(got, want)
+        assert int(csr.hub_done().abs().sum()) == 0
+    # wide rows (several feature blocks per row) keep the separate finalize kernel
+    xw = torch.randn(n, 640, generator=g).to(dev())
+    got = P.aggregate_forward(xw, csr, A4, S3, avg)
+    monkeypatch.setenv("PNA_B200_FOLD_FINALIZE", "0")
+    assert torch.equal(got, P.aggregate_forward(xw, csr, A4, S3, avg))
+
+
+# ---- per-graph readouts on the aggregation kernel (reference nets: dgl.sum/mean/max_nodes, global_mean_pool) ---------
+def test_readouts_match_torch_segment_ops(P):
+    from pna_b200 import readout as R
+    g = torch.Generator().manual_seed(41)
+    sizes = torch.cat([torch.randint(1, 40, (200,), generator=g), torch.tensor([0, 700, 0, 3])])    # empty + one split row
+    batch = torch.repeat_interleave(torch.arange(sizes.numel()), sizes)
+    n, b, f = int(sizes.sum()), sizes.numel(), 64
+    x = torch.randn(n, f, generator=g)
+    xd = x.to(dev()).requires_grad_(True)
+    bd = batch.to(dev())
+    want_sum = torch.zeros(b, f).index_add_(0, batch, x)
+    cnt = sizes.clamp(min=1).unsqueeze(1).float()
+    want_max = torch.zeros(b, f).scatter_reduce_(0, batch.unsqueeze(1).expand(-1, f), x, "amax", include_self=False)
+    # the 700-node graph is a split row: its sum is merged chunk-wise, torch's is sequential -> compare at sum-of-700 noise
+    torch.testing.assert_close(R.global_add_pool(xd, bd, b).detach().cpu(), want_sum, rtol=1e-5, atol=5e-5)
+    torch.testing.assert_close(R.global_mean_pool(xd, bd, b).detach().cpu(), want_sum / cnt, rtol=1e-5, atol=1e-5)
+    assert torch.equal(R.global_max_pool(xd, bd, b).detach().cpu(), want_max)
+    assert R.global_add_pool(xd, bd).shape == (b, f)               # size inferred from batch.max()
+    w = torch.randn(b, f, generator=g)
+    (R.global_mean_pool(xd, bd, b) * w.to(dev())).sum().backward()
+    torch.testing.assert_close(xd.grad.cpu(), (w / cnt)[batch], rtol=1e-5, atol=1e-6)
+    gr = P.Graph(torch.zeros(0, dtype=torch.long), torch.zeros(0, dtype=torch.long), n, batch_num_nodes=sizes.tolist()).to(dev())
+    gr.ndata["h"] = x.to(dev())
+    torch.testing.assert_close(R.sum_nodes(gr, "h").cpu(), want_sum, rtol=1e-5, atol=5e-5)
+    torch.testing.assert_close(R.mean_nodes(gr, "h").cpu(), want_sum / cnt, rtol=1e-5, atol=1e-5)
+    assert torch.equal(R.max_nodes(gr, "h").cpu(), want_max)
