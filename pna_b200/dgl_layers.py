@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from . import padding as pad
 from .aggregate import pna_aggregate, row_scales
-from .linear import scaled_kernel_applies
+from .linear import compact_path_ok
 from .graph import graph_csr
 from .nn_blocks import FCLayer, MLP
 
@@ -174,7 +174,7 @@ class PNASimpleLayer(nn.Module):
         if fp != self.in_dim:   # odd width: 128-bit path on zero-padded rows, padding absorbed by the first posttrans Linear
             w0 = pad.expand_weight_cols(w0, blocks, self.in_dim, fp)
         hp = pad.pad_cols(h, fp)
-        if h.size(0) > 0 and scaled_kernel_applies(h.new_empty((1, len(self.aggregators) * fp)), w0, len(self.scalers)):
+        if w0.dtype == torch.float32 and compact_path_ok(h, len(self.aggregators) * fp, w0.size(0), len(self.scalers)):
             # compact post path: identity-scaled aggregate, the scaled copies are formed inside the tensor-core linear
             agg = pna_aggregate(hp, csr, self.aggregators, ["identity"], self.avg_d, zero_isolated=True)
             h = self.posttrans(agg, first_weight=w0, first_row_scale=row_scales(csr, self.scalers, self.avg_d))

@@ -72,6 +72,13 @@ def post_linear(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
 # ---- compact path: a = identity-scaled aggregate [N, A*F], the S scaled copies exist only inside the kernel ----------
 
 
+def compact_path_ok(x: torch.Tensor, n_a: int, n_out: int, n_scalers: int) -> bool:
+    """Shape-level decision the layers take BEFORE aggregating: would a fresh fp32 [N, n_a] aggregate on x's device,
+    with a [n_out, n_scalers * n_a] first post Linear, go through pna_linear_scaled_fwd?"""
+    return (n_scalers > 1 and x.is_cuda and x.dtype == torch.float32 and x.size(0) > 0 and n_a % 32 == 0 and n_out in _OUT_OK
+            and os.environ.get("PNA_B200_TENSOR_LINEAR", "1") != "0" and os.environ.get("PNA_B200_COMPACT_POST", "1") != "0")
+
+
 def scaled_kernel_applies(a: torch.Tensor, weight: torch.Tensor, n_scalers: int) -> bool:
     return (n_scalers > 1 and kernel_applies(a, weight) and weight.size(1) == n_scalers * a.size(1)
             and os.environ.get("PNA_B200_COMPACT_POST", "1") != "0")

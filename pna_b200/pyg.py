@@ -15,7 +15,7 @@ from torch.nn import Linear, Module, ModuleList, ReLU, Sequential
 
 from . import padding as pad
 from .aggregate import avg_deg_from_histogram, pna_aggregate, row_scales
-from .linear import post_linear, post_linear_scaled, scaled_kernel_applies
+from .linear import compact_path_ok, post_linear, post_linear_scaled
 from .csr import CSRGraph, csr_from_edge_index
 
 _AGGRS = ("sum", "mean", "min", "max", "var", "std")          # aggregators.py:35-42
@@ -92,8 +92,9 @@ class PNAConvSimple(Module):
         """Compact post path: aggregate with the identity scaler only ([N, A*F]) and let the tensor-core
         linear regenerate the scaled copies in registers -- the [N, S*A*F] tensor is never written.  Same arithmetic."""
         Fp = pad.padded_width(self.F_in, x.dtype)
-        probe = x.new_empty((1, len(self.aggregators) * Fp))          # shape/dtype/device stand-in for the aggregate
-        return x.size(0) > 0 and scaled_kernel_applies(probe, self._first_weight(x.dtype), len(self.scalers))
+        lin0 = self.post_nn[0]
+        return lin0.weight.dtype == torch.float32 and compact_path_ok(x, len(self.aggregators) * Fp, lin0.out_features,
+                                                                      len(self.scalers))
 
     def _aggregate_padded(self, x: Tensor, csr: CSRGraph):
         """Aggregation at the kernel's 16-byte feature granularity: odd widths (e.g. 75) run on zero-padded rows.
