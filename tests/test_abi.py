@@ -80,3 +80,30 @@ def test_bad_arguments_return_status_codes_not_aborts():
 def test_product_refuses_cpu_tensors():
     with pytest.raises(ValueError):
         pna_b200.build_csr(torch.zeros(2, dtype=torch.long), torch.zeros(2, dtype=torch.long), 2)
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 (what a cgo / JNI / ctypes-generator binding consumes)."""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", "c", HEADER],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+
+
+def test_post_linear_entry_points_validate_without_gpu():
+    L = _lib.lib()
+    fwd, scaled, scales = L.pna_linear_fwd, L.pna_linear_scaled_fwd, L.pna_row_scales
+    assert fwd(None, 0, None, None, None, 0, 0, 64, 128, None, 0, None) == 0               # no rows: nothing to do
+    assert fwd(None, 0, None, None, None, 0, 5, 60, 128, None, 0, None) == -2              # n_in % 32
+    assert fwd(None, 0, None, None, None, 0, 5, 64, 100, None, 0, None) == -2              # n_out not 64/128/256
+    assert fwd(None, 0, None, None, None, 0, 5, 64, 128, None, 0, None) == -1              # null pointers
+    assert b"pna_linear_fwd" in L.pna_last_error()
+    assert scaled(None, 0, None, 3, None, None, None, 0, 0, 96, 64, None, 0, None) == 0
+    assert scaled(None, 0, None, 3, None, None, None, 0, 5, 96, 64, None, 0, None) == -1   # row_scale missing
+    assert scaled(None, 0, None, 3, None, None, None, 0, 0, 100, 64, None, 0, None) == -2  # 100 / 3 is not a K width
+    assert scaled(None, 0, None, 9, None, None, None, 0, 0, 288, 64, None, 0, None) == -1  # more scalers than exist
+    assert b"pna_linear_scaled_fwd" in L.pna_last_error()
+    assert scales(None, 0, 3, 0x210, 1.0, 1.0, None, None) == 0
+    assert scales(None, 7, 3, 0x210, 1.0, 1.0, None, None) == -1                           # null pointers
+    assert scales(None, 0, 2, 0x90, 1.0, 1.0, None, None) == -1                            # scaler code 9 does not exist
+    assert scales(None, 0, 0, 0, 1.0, 1.0, None, None) == -1
