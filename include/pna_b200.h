@@ -97,7 +97,7 @@ typedef struct pna_csr {
   int32_t* hub_info;        /* out [4*cap_hubs] */
   int32_t* chunk_items;     /* out [2*cap_chunks] */
   int64_t cap_hubs;         /* in: >= n_edges/split_threshold + 1 */
-  int64_t cap_chunks;       /* in: >= n_edges/chunk_edges + cap_hubs + 1 */
+  int64_t cap_chunks;       /* in: >= n_edges/chunk_edges + cap_hubs + 1 (and <= 2*n_edges + 3 when the light view is requested) */
   int64_t n_hubs;           /* out (host) */
   int64_t n_chunks;         /* out (host) */
   int32_t max_degree;       /* out (host) */

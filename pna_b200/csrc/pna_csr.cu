@@ -252,6 +252,10 @@ extern "C" int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* 
   PNA_REQUIRE(csr->cap_hubs >= E / csr->split_threshold + 1, PNA_ERR_WORKSPACE, "pna_csr_build: cap_hubs too small");
   PNA_REQUIRE(csr->cap_chunks >= E / csr->chunk_edges + csr->cap_hubs + 1, PNA_ERR_WORKSPACE, "pna_csr_build: cap_chunks too small");
   PNA_REQUIRE(csr->hub_info && csr->chunk_items, PNA_ERR_BAD_ARG, "pna_csr_build: null hub_info/chunk_items");
+  // the view scan runs over n_nodes + cap_chunks + 1 entries of workspace sized for n_nodes + 2 * n_edges + 4 (ws_layout)
+  PNA_REQUIRE(csr->light_rowptr == nullptr || csr->cap_chunks <= 2 * E + 3, PNA_ERR_BAD_ARG,
+              "pna_csr_build: cap_chunks %lld exceeds 2 * n_edges + 3 (the light view could not be scanned in the workspace)",
+              (long long)csr->cap_chunks);
   WsLayout L;
   int rc = ws_layout(N, E, &L);
   if (rc != PNA_OK) return rc;

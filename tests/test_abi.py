@@ -107,3 +107,16 @@ def test_post_linear_entry_points_validate_without_gpu():
     assert scales(None, 7, 3, 0x210, 1.0, 1.0, None, None) == -1                           # null pointers
     assert scales(None, 0, 2, 0x90, 1.0, 1.0, None, None) == -1                            # scaler code 9 does not exist
     assert scales(None, 0, 0, 0, 1.0, 1.0, None, None) == -1
+
+
+def test_csr_build_rejects_inconsistent_capacities_before_touching_the_gpu():
+    L = _lib.lib()
+    dummy = 256                                                   # never dereferenced: validation fails first
+    c = _lib.CsrStruct(n_nodes=10, n_edges=100, split_threshold=256, chunk_edges=128, rowptr=dummy, col=dummy, perm=dummy,
+                       hub_info=dummy, chunk_items=dummy, cap_hubs=1, cap_chunks=2, light_rowptr=dummy)
+    assert L.pna_csr_build(dummy, dummy, C.byref(c), None, 0, None) == -3 and b"workspace" in L.pna_last_error()   # sizes fine
+    c.cap_chunks = 10_000                                          # > 2 * n_edges + 3: the view scan would overrun the workspace
+    assert L.pna_csr_build(dummy, dummy, C.byref(c), None, 0, None) == -1
+    assert b"cap_chunks" in L.pna_last_error()
+    c.chunk_edges = 512                                            # chunk larger than the split threshold
+    assert L.pna_csr_build(dummy, dummy, C.byref(c), None, 0, None) == -1
