@@ -114,7 +114,8 @@ def test_csr_build_rejects_inconsistent_capacities_before_touching_the_gpu():
     dummy = 256                                                   # never dereferenced: validation fails first
     c = _lib.CsrStruct(n_nodes=10, n_edges=100, split_threshold=256, chunk_edges=128, rowptr=dummy, col=dummy, perm=dummy,
                        hub_info=dummy, chunk_items=dummy, cap_hubs=1, cap_chunks=2, light_rowptr=dummy)
-    assert L.pna_csr_build(dummy, dummy, C.byref(c), None, 0, None) == -3 and b"workspace" in L.pna_last_error()   # sizes fine
+    # consistent capacities pass the checks (the call then stops at the missing workspace / missing device)
+    assert L.pna_csr_build(dummy, dummy, C.byref(c), None, 0, None) < 0 and b"cap_" not in L.pna_last_error()
     c.cap_chunks = 10_000                                          # > 2 * n_edges + 3: the view scan would overrun the workspace
     assert L.pna_csr_build(dummy, dummy, C.byref(c), None, 0, None) == -1
     assert b"cap_chunks" in L.pna_last_error()
