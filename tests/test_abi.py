@@ -121,3 +121,19 @@ def test_csr_build_rejects_inconsistent_capacities_before_touching_the_gpu():
     assert b"cap_chunks" in L.pna_last_error()
     c.chunk_edges = 512                                            # chunk larger than the split threshold
     assert L.pna_csr_build(dummy, dummy, C.byref(c), None, 0, None) == -1
+
+
+def test_plain_c_caller_compiles_and_links():
+    """examples/c_caller.c drives the ABI from C99 with nothing but the header and the CUDA runtime."""
+    import subprocess, tempfile
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("CUDA toolkit headers not found")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "c_caller")
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                            os.path.join(ROOT, "examples", "c_caller.c"), "-o", exe, "-L", os.path.dirname(_lib.LIB_PATH),
+                            "-l:" + os.path.basename(_lib.LIB_PATH), "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+                            "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)], capture_output=True, text=True)
+        assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+        assert os.path.exists(exe)
