@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNA_ABI_VERSION 6
+#define PNA_ABI_VERSION 7
 
 typedef void* pna_stream_t; /* a cudaStream_t / CUstream, passed opaquely */
 
@@ -61,7 +61,11 @@ enum pna_flags {
                                   (models/dgl/pna_layer.py:64 update_all).  Default (PyG/torch_scatter semantics):
                                   mean=min=max=0, std=sqrt(1e-5), then scaled. */
   PNA_FLAG_SKIP_LIGHT = 2u,    /* do not process rows below the split threshold (used to overlap halo exchange) */
-  PNA_FLAG_SKIP_HUBS = 4u      /* do not process rows at/above the split threshold */
+  PNA_FLAG_SKIP_HUBS = 4u,     /* do not process rows at/above the split threshold */
+  PNA_FLAG_RELU_VAR = 8u       /* the "var" aggregator is clamped at 0 (models/dgl/aggregators.py:22-26 and
+                                  models/pytorch/pna/aggregators.py:63-76 apply torch.relu; the PyG flavour,
+                                  models/pytorch_geometric/aggregators.py:25-28, does not); its gradient is masked where
+                                  the raw variance is <= 0 */
 };
 
 enum pna_query_what {
@@ -204,6 +208,11 @@ typedef struct pna_agg {
    * also merges and finalizes it (same merge order as the separate finalize kernel), so a layer call is ONE launch with
    * no serial tail.  NULL: split rows are finalized by a second small kernel.  Not to be shared by concurrent calls. */
   int32_t* hub_done;
+  /* optional int32 [n_rows]: the degree the SCALERS see, when it is not the in-degree of the CSR row.  The dense reference
+   * layer aggregates over adj + I with self_loop=True but scales with D = adj.sum(-1) of the loop-free adjacency
+   * (models/pytorch/pna/scalers.py:13,21,28,35), and its max/min reduce over the other adjacency axis while still being
+   * scaled with the row degree.  NULL: scalers use rowptr[i+1] - rowptr[i] (PyG / DGL). */
+  const int32_t* scaler_degree;
 } pna_agg_t;
 
 int pna_aggregate_fwd(const pna_agg_t* desc, pna_stream_t stream);

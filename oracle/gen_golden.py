@@ -191,8 +191,62 @@ def multitask_case():
                                     avg_deg=conv.avg_deg, state_dict=conv.state_dict(), aggregate=agg, out=out))
 
 
+def round2_cases():
+    """Fixtures added in round 2 (the earlier ones are not regenerated): the flavours' relu(var) and the dense layer with
+    self_loop=True on a DIRECTED adjacency, where row and column degrees differ."""
+    # DGL simple layer with "var" and ZINC-like identical neighbour rows: E[m^2] - E[m]^2 cancels to +-1 ulp noise, the
+    # reference's torch.relu (models/dgl/aggregators.py:22-26) turns the negative ones into exact zeros
+    torch.manual_seed(21)
+    n, e, f = 80, 360, 12
+    ei = graph_random(n, e, 21)
+    table = torch.randn(3, f) * 3.0
+    h = table[torch.randint(0, 3, (n,))]
+    indeg = torch.bincount(ei[1], minlength=n).float()
+    avg_d = dict(lin=indeg.mean().item(), exp=torch.exp(indeg).mean().item(), log=torch.log(indeg + 1).mean().item())
+    aggr, scal = "mean max min std var", "identity amplification attenuation"
+    lay = DGLPNASimpleLayer(f, f, aggr, scal, avg_d, dropout=0.0, batch_norm=True, residual=True, posttrans_layers=1)
+    lay.eval()
+    g = dgl.DGLGraph(ei[0], ei[1], n)
+    with torch.no_grad():
+        g.ndata["h"] = h
+        g.update_all(dgl.function.copy_u("h", "m"), lay.reduce_func)
+        agg = g.ndata["h"].clone()
+        out = lay(dgl.DGLGraph(ei[0], ei[1], n), h)
+    save("dgl_simple_var", dict(kind="dgl_simple", h=h, edge_index=ei, avg_d=avg_d, aggregators=aggr, scalers=scal,
+                                ctor=dict(in_dim=f, out_dim=f, dropout=0.0, batch_norm=True, residual=True, posttrans_layers=1),
+                                state_dict=lay.state_dict(), aggregate=agg, out=out))
+    # dense layer, self_loop=True, aggregators incl. var, directed 0/1 adjacency without empty rows or columns
+    torch.manual_seed(22)
+    B, n, f = 2, 14, 8
+    adj = (torch.rand(B, n, n) < 0.25).float()
+    adj = adj * (1 - torch.eye(n))                       # the layer adds the loop itself
+    for b in range(B):
+        for i in range(n):
+            if adj[b, i].sum() == 0:
+                adj[b, i, (i + 1) % n] = 1
+            if adj[b, :, i].sum() == 0:
+                adj[b, (i + 2) % n, i] = 1
+    table = torch.rand(3, f)
+    hd = table[torch.randint(0, 3, (B, n))]
+    hd[:, ::3] = torch.rand(B, (n + 2) // 3, f)         # a mix of identical and distinct rows
+    avg_dd = dict(lin=adj.sum(-1).mean().item(), log=torch.log(adj.sum(-1) + 1).mean().item())
+    aggrs = ["mean", "max", "min", "std", "var"]
+    for name, loop in (("dense_self_loop", True), ("dense_directed", False)):
+        layd = DensePNALayer(f, f, aggrs, S3, avg_dd, towers=2, self_loop=loop, pretrans_layers=1, posttrans_layers=1,
+                             divide_input=True)
+        layd.eval()
+        with torch.no_grad():
+            outd = layd(hd, adj)
+        save(name, dict(kind="dense", adj=adj, h=hd, avg_d=avg_dd, aggregators=aggrs, scalers=S3,
+                        ctor=dict(in_features=f, out_features=f, towers=2, self_loop=loop, pretrans_layers=1,
+                                  posttrans_layers=1, divide_input=True), state_dict=layd.state_dict(), out=outd))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--round2" in sys.argv:
+        round2_cases()
+        sys.exit(0)
     simple_case("pyg_simple_f16", 200, 900, 16, seed=1)
     simple_case("pyg_simple_f64_hub", 100, 400, 64, seed=2, hub=700)
     simple_case("pyg_simple_f75_const", 90, 260, 75, seed=3, aggrs=A4_EX, constant_rows=True)

@@ -37,6 +37,12 @@ def _rows2d(t: torch.Tensor, what: str) -> torch.Tensor:
     return t
 
 
+def _check_scaler_degree(t: torch.Tensor, n_rows: int, dev) -> torch.Tensor:
+    if t.dtype != torch.int32 or t.device != dev or t.numel() != n_rows or not t.is_contiguous():
+        raise ValueError("scaler_degree must be a contiguous int32 [n_rows] tensor on the same device")
+    return t
+
+
 def fold_finalize_enabled() -> bool:
     """PNA_B200_FOLD_FINALIZE=1: the warp that completes a split row also finalizes it (one launch per call)."""
     return os.environ.get("PNA_B200_FOLD_FINALIZE", "0") == "1"
@@ -49,9 +55,10 @@ def output_width(n_feat: int, n_aggr: int, n_scalers: int, has_self: bool) -> in
 def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names, scalers: Names,
                       avg_deg: Mapping[str, float], *, towers: int = 1, row_bias: Optional[torch.Tensor] = None,
                       self_feat: Optional[torch.Tensor] = None, self_divided: bool = True,
-                      messages_in_csr_order: bool = False, zero_isolated: bool = False,
+                      messages_in_csr_order: bool = False, zero_isolated: bool = False, relu_var: bool = False,
                       out: Optional[torch.Tensor] = None, row_ids: Optional[torch.Tensor] = None,
-                      skip_light: bool = False, skip_hubs: bool = False, view=None, peer=None) -> torch.Tensor:
+                      skip_light: bool = False, skip_hubs: bool = False, view=None, peer=None,
+                      scaler_degree: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Run the CUDA aggregation (no autograd).  Returns ``[N, towers * (has_self + S*A) * Ft]``.
 
     gathered : [n_src, F] rows that are gathered through ``csr.col`` (x for PNAConvSimple; V = x W_j^T + b for
@@ -99,7 +106,7 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
         if row_ids.dtype != torch.int32 or not row_ids.is_contiguous() or row_ids.device != dev:
             raise ValueError("row_ids must be a contiguous int32 tensor on the same device")
     flags = (_lib.FLAG_ZERO_ISOLATED if zero_isolated else 0) | (_lib.FLAG_SKIP_LIGHT if skip_light else 0) | \
-            (_lib.FLAG_SKIP_HUBS if skip_hubs else 0)
+            (_lib.FLAG_SKIP_HUBS if skip_hubs else 0) | (_lib.FLAG_RELU_VAR if relu_var else 0)
     partials = None if skip_hubs else csr.hub_partials(F)
     d = _lib.AggStruct(
         gathered=_ptr(gathered), ld_gathered=gathered.stride(0) if gathered.size(0) > 1 else F,
@@ -115,6 +122,8 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
         hub_info=_ptr(csr.hub_info) if csr.n_hubs else None, chunk_items=_ptr(csr.chunk_items) if csr.n_hubs else None,
         n_hubs=csr.n_hubs, n_chunks=csr.n_chunks, hub_partials=_ptr(partials),
         row_ids=_ptr(row_ids), n_row_ids=0 if row_ids is None else int(row_ids.numel()))
+    if scaler_degree is not None:
+        d.scaler_degree = _check_scaler_degree(scaler_degree, N, dev).data_ptr()
     if view is None and row_ids is None:
         view = csr.full_view()
         if fold_finalize_enabled() and not skip_hubs and peer is None:
@@ -159,7 +168,8 @@ def row_scales(csr: CSRGraph, scalers: Names, avg_deg: Mapping[str, float]) -> t
 # ---- autograd ----------------------------------------------------------------------------------------------------
 def aggregate_backward(grad_out: torch.Tensor, gathered: torch.Tensor, csr: CSRGraph, aggregators: Names, scalers: Names,
                        avg_deg: Mapping[str, float], *, towers: int = 1, row_bias: Optional[torch.Tensor] = None,
-                       has_self: bool = False, messages_in_csr_order: bool = False, need_bias_grad: bool = False):
+                       has_self: bool = False, messages_in_csr_order: bool = False, need_bias_grad: bool = False,
+                       relu_var: bool = False, scaler_degree: Optional[torch.Tensor] = None):
     """Gradient of the aggregation w.r.t. ``gathered`` (and ``row_bias``) through ``pna_aggregate_bwd`` (fp32 results)."""
     dev = gathered.device
     gathered = _rows2d(gathered, "gathered")
@@ -180,9 +190,12 @@ def aggregate_backward(grad_out: torch.Tensor, gathered: torch.Tensor, csr: CSRG
         n_rows=N, n_feat=F, n_towers=towers, dtype=_DTYPES[gathered.dtype],
         n_aggr=n_aggr, aggr_codes=aggr_codes, n_scalers=n_scal, scaler_codes=scal_codes,
         avg_log=float(avg_deg["log"]), avg_lin=float(avg_deg.get("lin", 1.0)),
+        flags=_lib.FLAG_RELU_VAR if relu_var else 0,
         split_threshold=csr.split_threshold, chunk_edges=csr.chunk_edges,
         hub_info=_ptr(csr.hub_info) if csr.n_hubs else None, chunk_items=_ptr(csr.chunk_items) if csr.n_hubs else None,
         n_hubs=csr.n_hubs, n_chunks=csr.n_chunks)
+    if scaler_degree is not None:
+        d.scaler_degree = _check_scaler_degree(scaler_degree, N, dev).data_ptr()
     scratch = None
     if csr.n_hubs:   # per-chunk statistics + per-split-row coefficients
         scratch = torch.empty(((csr.n_chunks + csr.n_hubs) * 6, F), dtype=torch.float32, device=dev)
@@ -196,21 +209,24 @@ def aggregate_backward(grad_out: torch.Tensor, gathered: torch.Tensor, csr: CSRG
 class _PNAAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gathered, row_bias, self_feat, csr, aggregators, scalers, avg_deg, towers, self_divided,
-                messages_in_csr_order, zero_isolated):
+                messages_in_csr_order, zero_isolated, relu_var=False, scaler_degree=None):
         out = aggregate_forward(gathered, csr, aggregators, scalers, avg_deg, towers=towers, row_bias=row_bias,
                                 self_feat=self_feat, self_divided=self_divided,
-                                messages_in_csr_order=messages_in_csr_order, zero_isolated=zero_isolated)
+                                messages_in_csr_order=messages_in_csr_order, zero_isolated=zero_isolated, relu_var=relu_var,
+                                scaler_degree=scaler_degree)
         ctx.save_for_backward(gathered, row_bias, self_feat)
-        ctx.meta = (csr, _names(aggregators), _names(scalers), dict(avg_deg), towers, self_divided, messages_in_csr_order)
+        ctx.meta = (csr, _names(aggregators), _names(scalers), dict(avg_deg), towers, self_divided, messages_in_csr_order,
+                    relu_var, scaler_degree)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         gathered, row_bias, self_feat = ctx.saved_tensors
-        csr, aggregators, scalers, avg_deg, towers, self_divided, in_order = ctx.meta
+        csr, aggregators, scalers, avg_deg, towers, self_divided, in_order, relu_var, scaler_degree = ctx.meta
         grad_g, grad_b = aggregate_backward(
             grad_out, gathered, csr, aggregators, scalers, avg_deg, towers=towers, row_bias=row_bias,
-            has_self=self_feat is not None, messages_in_csr_order=in_order, need_bias_grad=ctx.needs_input_grad[1])
+            has_self=self_feat is not None, messages_in_csr_order=in_order, need_bias_grad=ctx.needs_input_grad[1],
+            relu_var=relu_var, scaler_degree=scaler_degree)
         gs = None
         if self_feat is not None and ctx.needs_input_grad[2]:
             # the self block of every tower is a plain copy: its gradient is the matching slice of grad_out
@@ -220,22 +236,24 @@ class _PNAAggregate(torch.autograd.Function):
             gs = (blk.reshape(N, F) if self_divided else blk.sum(1)).to(self_feat.dtype)
         return (grad_g.to(gathered.dtype) if ctx.needs_input_grad[0] else None,
                 grad_b.to(row_bias.dtype) if (grad_b is not None) else None, gs,
-                None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None)
 
 
 def pna_aggregate(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names, scalers: Names,
                   avg_deg: Mapping[str, float], *, towers: int = 1, row_bias: Optional[torch.Tensor] = None,
                   self_feat: Optional[torch.Tensor] = None, self_divided: bool = True,
-                  messages_in_csr_order: bool = False, zero_isolated: bool = False) -> torch.Tensor:
+                  messages_in_csr_order: bool = False, zero_isolated: bool = False, relu_var: bool = False,
+                  scaler_degree: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Differentiable PNA aggregation (forward = one libpna_sm100 call).  See :func:`aggregate_forward`."""
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (gathered, row_bias, self_feat))
     if not needs_grad:
         return aggregate_forward(gathered, csr, aggregators, scalers, avg_deg, towers=towers, row_bias=row_bias,
                                  self_feat=self_feat, self_divided=self_divided,
-                                 messages_in_csr_order=messages_in_csr_order, zero_isolated=zero_isolated)
+                                 messages_in_csr_order=messages_in_csr_order, zero_isolated=zero_isolated, relu_var=relu_var,
+                                 scaler_degree=scaler_degree)
     return _PNAAggregate.apply(gathered, row_bias, self_feat, csr, aggregators, scalers, avg_deg, towers, self_divided,
-                               messages_in_csr_order, zero_isolated)
+                               messages_in_csr_order, zero_isolated, relu_var, scaler_degree)
 
 
 def avg_deg_from_histogram(deg: torch.Tensor) -> dict:

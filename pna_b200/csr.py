@@ -184,6 +184,12 @@ _CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 _CACHE_SIZE = 16
 
 
+def tensor_version(t: torch.Tensor):
+    """In-place version counter for cache keys; inference-mode tensors do not track one (reading ``_version`` raises), and
+    cannot be modified in place outside inference mode either, so a constant stands in for it."""
+    return None if t.is_inference() else t._version
+
+
 def csr_from_edge_index(edge_index: torch.Tensor, n_nodes: int, cache: bool = True) -> CSRGraph:
     """CSR of a PyG ``edge_index`` (row 0 = source j, row 1 = target i; aggregation index = row 1).
 
@@ -192,7 +198,7 @@ def csr_from_edge_index(edge_index: torch.Tensor, n_nodes: int, cache: bool = Tr
     """
     if edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise ValueError("edge_index must have shape [2, E]")
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), tuple(edge_index.stride()), int(n_nodes),
+    key = (edge_index.data_ptr(), tensor_version(edge_index), tuple(edge_index.shape), tuple(edge_index.stride()), int(n_nodes),
            str(edge_index.device))
     if cache:
         hit = _CACHE.get(key)

@@ -97,6 +97,15 @@ struct Io<float, 4> {
 };
 
 template <>
+struct Io<float, 2> {
+  typedef float2 Raw;
+  static __device__ __forceinline__ Raw load_raw(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[2]) { v[0] = r.x; v[1] = r.y; }
+  static __device__ __forceinline__ void load(const float* p, float (&v)[2]) { unpack(load_raw(p), v); }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[2]) { __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1])); }
+};
+
+template <>
 struct Io<float, 1> {
   typedef float Raw;
   static __device__ __forceinline__ Raw load_raw(const float* p) { return __ldg(p); }

@@ -36,6 +36,8 @@ struct KParams {
   const int* row_ids; long long n_row_ids;
   const int* lrowptr; const int* ldeg; const int* lcol; const int* part; int n_part;   // light view (nullable)
   long long n_view_rows;   // > n_rows: view rows n_rows + c are chunk pseudo-rows reduced into partials[c]
+  const int* sdeg;         // nullable [n_rows]: degree seen by the scalers (default: the in-degree of the row)
+  int n_fpass;             // > 1: the streamed kernel makes this many passes over its rows, one feature block each
   const void* const* peer_x; int peer_shift;   // multi-GPU: x of every rank (NVLink peer pointers), col = owner << shift | row
 };
 
@@ -252,7 +254,8 @@ __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC
   const bool iso = deg == 0;
   const float degf = (float)deg;
   const float cnt = iso ? 1.0f : degf;                     // count.clamp_(1)
-  const DegScales ds = deg_scales(deg, p.avg_log, p.avg_lin);   // unused factors are dead code under a static Cfg
+  // unused factors are dead code under a static Cfg; the scalers' degree may be supplied separately (dense layer)
+  const DegScales ds = deg_scales(p.sdeg ? __ldg(p.sdeg + row) : deg, p.avg_log, p.avg_lin);
   const bool zero_all = iso && (p.flags & PNA_FLAG_ZERO_ISOLATED);
   const int nA = Cfg::kStatic ? Cfg::NA : p.nA, nS = Cfg::kStatic ? Cfg::NS : p.nS;
   const unsigned acodes = Cfg::kStatic ? Cfg::ACODES : p.acodes, scodes = Cfg::kStatic ? Cfg::SCODES : p.scodes;
@@ -291,7 +294,7 @@ __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC
           case PNA_AGGR_MEAN: r = mean[i]; break;
           case PNA_AGGR_MIN: r = mn[i]; break;
           case PNA_AGGR_MAX: r = mx[i]; break;
-          case PNA_AGGR_VAR: r = var[i]; break;
+          case PNA_AGGR_VAR: r = (p.flags & PNA_FLAG_RELU_VAR) ? fmaxf(var[i], 0.0f) : var[i]; break;
           default: r = sd[i]; break;
         }
         val[i] = zero_all ? 0.0f : r;

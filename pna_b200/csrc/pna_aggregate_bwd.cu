@@ -62,9 +62,12 @@ __device__ __forceinline__ void coefficients(const BParams& b, long long row, in
   const KParams& p = b.k;
   const bool iso = deg == 0;
   const float degf = (float)deg, cnt = iso ? 1.0f : degf;
-  const float lg = logf(degf + 1.0f);
-  const float s_amp = lg / p.avg_log, s_att = iso ? 1.0f : p.avg_log / lg;
-  const float s_lin = degf / p.avg_lin, s_ilin = iso ? 1.0f : p.avg_lin / degf;
+  const int sdeg = p.sdeg ? __ldg(p.sdeg + row) : deg;      // degree seen by the scalers (pna_agg_t.scaler_degree)
+  const bool siso = sdeg == 0;
+  const float sdegf = (float)sdeg;
+  const float lg = logf(sdegf + 1.0f);
+  const float s_amp = lg / p.avg_log, s_att = siso ? 1.0f : p.avg_log / lg;
+  const float s_lin = sdegf / p.avg_lin, s_ilin = siso ? 1.0f : p.avg_lin / sdegf;
   const T* __restrict__ gorow = static_cast<const T*>(b.go) + row * b.ldgo + ooff;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) { c.c0[i] = 0.f; c.c1[i] = 0.f; c.gmin[i] = 0.f; c.gmax[i] = 0.f; }
@@ -97,7 +100,10 @@ __device__ __forceinline__ void coefficients(const BParams& b, long long row, in
         case PNA_AGGR_MEAN: c.c0[i] += g[i] / cnt; break;
         case PNA_AGGR_MIN: c.gmin[i] += g[i]; break;
         case PNA_AGGR_MAX: c.gmax[i] += g[i]; break;
-        case PNA_AGGR_VAR: { const float t = 2.0f * g[i] / cnt; c.c1[i] += t; c.c0[i] -= t * mean[i]; } break;
+        case PNA_AGGR_VAR: {   // relu'(var) = [var > 0] in the DGL / dense flavours (PNA_FLAG_RELU_VAR)
+          const float t = ((p.flags & PNA_FLAG_RELU_VAR) && !(var[i] > 0.f)) ? 0.f : 2.0f * g[i] / cnt;
+          c.c1[i] += t; c.c0[i] -= t * mean[i];
+        } break;
         default: { const float t = var[i] > 0.f ? g[i] / (cnt * sd[i]) : 0.f; c.c1[i] += t; c.c0[i] -= t * mean[i]; } break;
       }
     }
@@ -435,6 +441,7 @@ extern "C" int pna_aggregate_bwd(const pna_agg_t* d, const void* grad_out, int64
   p.flags = d->flags; p.split = d->split_threshold; p.chunk = d->chunk_edges;
   p.hub_info = d->hub_info; p.n_hubs = d->n_hubs; p.chunk_items = d->chunk_items; p.n_chunks = d->n_chunks;
   p.partials = d->hub_partials;
+  p.sdeg = d->scaler_degree;
   b.go = grad_out; b.ldgo = ld_grad_out;
   b.gg = grad_gathered; b.ldgg = ld_grad_gathered;
   b.gb = grad_row_bias; b.ldgb = ld_grad_row_bias;

@@ -2,6 +2,8 @@
 // pna_aggregate_{f32,bf16}_{vec,scalar}.cu so the translation units compile in parallel.
 #pragma once
 #include "pna_aggregate.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace pna {
 
@@ -256,12 +258,18 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 // 128-bit shared-memory load through a 32-bit shared address (no generic-address conversion in the loop)
 template <typename T, int VEC>
 __device__ __forceinline__ typename Io<T, VEC>::Raw lds_raw(unsigned addr) {
-  static_assert(sizeof(typename Io<T, VEC>::Raw) == 16, "stream path moves 128-bit chunks");
-  unsigned a, b, c, d;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+  static_assert(sizeof(typename Io<T, VEC>::Raw) == 16 || sizeof(typename Io<T, VEC>::Raw) == 8, "stream path moves 128- or 64-bit chunks");
   typename Io<T, VEC>::Raw r;
   unsigned* w = reinterpret_cast<unsigned*>(&r);
-  w[0] = a; w[1] = b; w[2] = c; w[3] = d;
+  if constexpr (sizeof(typename Io<T, VEC>::Raw) == 16) {
+    unsigned a, b, c, d;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+    w[0] = a; w[1] = b; w[2] = c; w[3] = d;
+  } else {
+    unsigned a, b;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
+    w[0] = a; w[1] = b;
+  }
   return r;
 }
 
@@ -283,6 +291,15 @@ struct StreamGeom {
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src, unsigned long long policy) {
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "l"(policy)
                : "memory");
+}
+// 8-byte variant (feature-split passes: 64-bit chunks per lane); .ca is the only qualifier cp.async allows below 16 bytes
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src, unsigned long long policy) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "l"(policy)
+               : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_chunk(unsigned dst, const void* src, unsigned long long policy) {
+  if constexpr (BYTES == 16) cp_async16(dst, src, policy); else cp_async8(dst, src, policy);
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -444,7 +461,13 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
 #endif
 
   const int* __restrict__ lcol = p.lcol + Q0;
-  const int fblock = blockIdx.y * (G * VEC * K);
+  // feature passes: with n_fpass > 1 every warp walks its rows n_fpass times, each time over a block of G*VEC*K
+  // features -- the gathered working set of a pass is n_src * (block bytes), sized to stay L2-resident
+  constexpr int CB = VEC * (int)sizeof(T);          // bytes per lane chunk (16, or 8 on the feature-split path)
+  const int n_fpass = p.n_fpass > 1 ? p.n_fpass : 1;
+#pragma unroll 1
+ for (int fpass = 0; fpass < n_fpass; ++fpass) {
+  const int fblock = (blockIdx.y * n_fpass + fpass) * (G * VEC * K);
   const unsigned copy_bytes = (unsigned)(min(G * VEC * K, p.F - fblock) * (int)sizeof(T));
   (void)copy_bytes;
   FeatMap<VEC, G, K> fm;
@@ -466,7 +489,7 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   const int lane_elems = fblock + lane * VEC;   // this lane's first 16-byte chunk inside a gathered row
   auto issue_half = [&](int n, int src) {
     const int nvalid = min(H, Te - n * H);
-    unsigned dst = ring + (unsigned)((n & 1) * H) * SLOT + lane * 16;
+    unsigned dst = ring + (unsigned)((n & 1) * H) * SLOT + lane * CB;
 #pragma unroll
     for (int u = 0; u < H; ++u, dst += SLOT) {
       const int s_u = __shfl_sync(FULL, src, u);
@@ -474,7 +497,7 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
         const T* sp = gathered_row<T>(p, s_u) + lane_elems;
 #pragma unroll
         for (int k = 0; k < K; ++k)
-          if (fm.ok[k]) cp_async16(dst + k * 512, sp + k * (32 * VEC), keep);
+          if (fm.ok[k]) cp_async_chunk<CB>(dst + k * (32 * CB), sp + k * (32 * VEC), keep);
       }
     }
     cp_async_commit();
@@ -507,7 +530,7 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   };
   int dg = load_deg(pa), rid = load_rid(pa);
 
-  const unsigned lane_off = (unsigned)lane * 16u;
+  const unsigned lane_off = (unsigned)lane * (unsigned)CB;
   int q = 0;   // stream position being consumed
 #pragma unroll 1
   for (int r0 = pa; r0 < pb; r0 += 32) {
@@ -552,8 +575,8 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
           for (int k = 0; k < K; ++k) {
             if (fm.ok[k]) {
               float m0[VEC], m1[VEC];
-              Io<T, VEC>::unpack(lds_raw<T, VEC>(sp + k * 512), m0);
-              Io<T, VEC>::unpack(lds_raw<T, VEC>(sp + SLOT + k * 512), m1);
+              Io<T, VEC>::unpack(lds_raw<T, VEC>(sp + k * (32 * CB)), m0);
+              Io<T, VEC>::unpack(lds_raw<T, VEC>(sp + SLOT + k * (32 * CB)), m1);
               acc[k].template add2<BIAS>(m0, m1, bias[BIAS ? k : 0]);
             }
           }
@@ -563,7 +586,7 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
           for (int k = 0; k < K; ++k) {
             if (fm.ok[k]) {
               float m0[VEC];
-              Io<T, VEC>::unpack(lds_raw<T, VEC>(sp + k * 512), m0);
+              Io<T, VEC>::unpack(lds_raw<T, VEC>(sp + k * (32 * CB)), m0);
               acc[k].template add1<BIAS>(m0, bias[BIAS ? k : 0]);
             }
           }
@@ -601,6 +624,10 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
     }
     dg = dgN; rid = ridN;
   }
+#if !PNA_STREAM_TMA
+  if (n_fpass > 1) { cp_async_wait<0>(); __syncwarp(); }
+#endif
+ }  // feature passes
 }
 
 // ---- hubs, pass 1: one lane group per chunk of `chunk` slots -> fp32 partials ------------------------------
@@ -682,6 +709,19 @@ __global__ void __launch_bounds__(kFinGroups * 32) k_hub_finalize(const KParams 
 }
 
 // ---- host dispatch -----------------------------------------------------------------------------------------
+// Feature-split streamed kernel for fp32 rows of 128 features (pna_aggregate_f32_fsplit.cu): 64-bit lane chunks,
+// two passes of 64 features.  Returns PNA_OK after launching, or > 0 when the shape is not one it takes.
+int launch_stream_fsplit_f32(const KParams& p, cudaStream_t st);
+// tuning knob (experiments only): PNA_B200_FEAT_SPLIT = "tiled2" | "stream2"
+static inline int feat_split_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("PNA_B200_FEAT_SPLIT");
+    mode = !e ? 0 : (!strcmp(e, "tiled2") ? 1 : (!strcmp(e, "stream2") ? 2 : 0));
+  }
+  return mode;
+}
+
 template <typename T, int VEC, int G, int K, int U>
 static int launch_config(const KParams& p_in, cudaStream_t st) {
   constexpr int RPW = 32 / G;
@@ -702,7 +742,19 @@ static int launch_config(const KParams& p_in, cudaStream_t st) {
       // identity scaler only: the compact [N, A*F] result consumed by pna_linear_scaled_fwd
       const bool s1 = p.nS == 1 && (p.scodes & 0xfu) == PNA_SCALE_IDENTITY && p.nA == 4;
       const int cfg = (p.acodes & 0xffffu) != CfgMeanMaxMinStd::ACODES ? 0 : s3 ? 1 : s1 ? 2 : 0;
-      if (G == 32 && VEC > 1 && p.lrowptr != nullptr && p.col != nullptr) {
+      bool fsplit_done = false;
+      if constexpr (G == 32 && VEC == 4 && K == 1 && sizeof(T) == 4) {
+        if (feat_split_mode() == 2 && p.lrowptr != nullptr && p.col != nullptr && p.peer_x == nullptr && p.bias == nullptr &&
+            cfg == 1 && p.F == 128) {
+          p.hub_done = nullptr;
+          const int rc = launch_stream_fsplit_f32(p, st);
+          if (rc < 0) return rc;
+          fsplit_done = rc == 0;
+          if (fsplit_done) chunks_in_stream = p.n_view_rows > p.n_rows;
+        }
+      }
+      if (fsplit_done) {
+      } else if (G == 32 && VEC > 1 && p.lrowptr != nullptr && p.col != nullptr) {
        if constexpr (G == 32 && VEC > 1) {
         // streamed gather over the light view, persistent warps
         const bool b = p.bias != nullptr;
@@ -786,6 +838,7 @@ int launch_typed(const KParams& p, cudaStream_t st) {
   if (chunks <= 4) return launch_config<T, VEC, 4, 1, 4>(p, st);
   if (chunks <= 8) return launch_config<T, VEC, 8, 1, 4>(p, st);
   if (chunks <= 16) return launch_config<T, VEC, 16, 1, 4>(p, st);
+  if (chunks == 32 && feat_split_mode() == 1) return launch_config<T, VEC, 16, 1, 4>(p, st);   // two feature blocks (gridDim.y)
   if (chunks <= 32) return launch_config<T, VEC, 32, 1, 4>(p, st);
   if (chunks <= 64) return launch_config<T, VEC, 32, 2, 2>(p, st);
   if (chunks <= 96) return launch_config<T, VEC, 32, 3, 2>(p, st);

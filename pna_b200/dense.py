@@ -11,6 +11,8 @@ aggregators.py:39,51) while ``mean/std/sum`` reduce over dim 2, so for node v
     mean/std see  pretrans([h_v, h_u])  over u with adj[v,u] != 0      (self first)
     max/min  see  pretrans([h_u, h_v])  over u with adj[u,v] >  0      (neighbour first)
 Two kernel calls fill one output row (PNA_AGGR_SKIP keeps the other call's column slots).
+``self_loop=True`` aggregates over adj + I while the scalers keep the loop-free row degree (``pna_agg_t.scaler_degree``);
+``var`` is clamped at 0 as the reference does (PNA_FLAG_RELU_VAR).
 Restrictions (documented, not silent): 0/1 adjacency (the reference's weighted sums are not reproduced), aggregators
 mean/max/min/std/sum/var, and -- unlike the reference, which divides by zero -- isolated nodes get PyG semantics.
 """
@@ -20,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from .aggregate import aggregate_forward, pna_aggregate
-from .csr import build_csr
+from .csr import build_csr, tensor_version
 from .nn_blocks import FCLayer, MLP
 
 _SELF_FIRST = ("mean", "std", "sum", "var")
@@ -38,6 +40,9 @@ class DenseGraphs:
         b, i, j = (a != 0).nonzero(as_tuple=True)
         off = b * N
         self.B, self.N = B, N
+        # the scalers always see D = adj.sum(-1) of the ORIGINAL adjacency (models/pytorch/pna/scalers.py:13,21,28,35): no
+        # self loop, row degree -- also for the max/min blocks, which reduce over the other axis
+        self.scaler_degree = (adj != 0).sum(-1).reshape(B * N).to(torch.int32).contiguous()
         self.row = build_csr(j + off, i + off, B * N)        # destination i, sources j with adj[i, j] != 0
         self.colwise = build_csr(i + off, j + off, B * N)    # destination j, sources i with adj[i, j] != 0
 
@@ -46,7 +51,7 @@ _CACHE = {}
 
 
 def dense_graphs(adj: torch.Tensor, self_loop: bool) -> DenseGraphs:
-    key = (adj.data_ptr(), adj._version, tuple(adj.shape), bool(self_loop), str(adj.device))
+    key = (adj.data_ptr(), tensor_version(adj), tuple(adj.shape), bool(self_loop), str(adj.device))
     hit = _CACHE.get(key)
     if hit is None:
         if len(_CACHE) > 8:
@@ -124,7 +129,8 @@ class PNALayer(nn.Module):
         A, Bm, b = self._halves(h)
         a1 = [a if a in _SELF_FIRST else "_skip" for a in self.aggregators]
         a2 = [a if a in _NBR_FIRST else "_skip" for a in self.aggregators]
-        common = dict(towers=T, self_feat=h, self_divided=self.divide_input)
+        common = dict(towers=T, self_feat=h, self_divided=self.divide_input, relu_var=True,
+                      scaler_degree=graphs.scaler_degree)
         need_grad = torch.is_grad_enabled() and (h.requires_grad or any(p.requires_grad for p in self.parameters()))
         both = any(a != "_skip" for a in a2) and any(a != "_skip" for a in a1)
         if not need_grad:
@@ -139,8 +145,8 @@ class PNALayer(nn.Module):
             if any(a != "_skip" for a in a2):
                 out2 = pna_aggregate(A + b, graphs.colwise, a2, self.scalers, self.avg_d, row_bias=Bm, **common)
                 out = torch.where(self._second_call_columns(out.size(1), a2, h.device), out2, out) if both else out2
-        # NB the scalers of the second call use the column degree; the reference scales every block with the ROW
-        # degree D = adj.sum(-1) (scalers.py:13,21).  They coincide for the symmetric adjacencies of the benchmark.
+        # both calls scale with the ROW degree D = adj.sum(-1) of the loop-free adjacency (scaler_degree), as
+        # models/pytorch/pna/scalers.py:13,21 does, whatever edge set the aggregators reduced over
         out = out.view(B * N, T, -1)
         y = torch.cat([tw.posttrans(out[:, t]) for t, tw in enumerate(self.towers)], dim=1)
         return self.mixing_network(y).view(B, N, -1)

@@ -129,7 +129,7 @@ class PNALayer(nn.Module):
             h_self = pad.pad_blocks(h, T, it, fp)
         else:
             h_self = pad.pad_cols(h, fp)
-        common = dict(towers=T, self_feat=h_self, self_divided=self.divide_input, zero_isolated=True)
+        common = dict(towers=T, self_feat=h_self, self_divided=self.divide_input, zero_isolated=True, relu_var=True)
         if not self.edge_features and self.towers[0].pretrans.is_single_affine():
             U, V = self._affine_terms(h, fp)
             agg = pna_aggregate(V, csr, self.aggregators, self.scalers, self.avg_d, row_bias=U, **common)
@@ -163,7 +163,7 @@ class PNASimpleLayer(nn.Module):
         self.avg_d = _avg(avg_d)
 
     def aggregate_only(self, g, h):
-        return pna_aggregate(h, graph_csr(g, h.device), self.aggregators, self.scalers, self.avg_d, zero_isolated=True)
+        return pna_aggregate(h, graph_csr(g, h.device), self.aggregators, self.scalers, self.avg_d, zero_isolated=True, relu_var=True)
 
     def forward(self, g, h):
         h_in = h
@@ -176,10 +176,10 @@ class PNASimpleLayer(nn.Module):
         hp = pad.pad_cols(h, fp)
         if w0.dtype == torch.float32 and compact_path_ok(h, len(self.aggregators) * fp, w0.size(0), len(self.scalers)):
             # compact post path: identity-scaled aggregate, the scaled copies are formed inside the tensor-core linear
-            agg = pna_aggregate(hp, csr, self.aggregators, ["identity"], self.avg_d, zero_isolated=True)
+            agg = pna_aggregate(hp, csr, self.aggregators, ["identity"], self.avg_d, zero_isolated=True, relu_var=True)
             h = self.posttrans(agg, first_weight=w0, first_row_scale=row_scales(csr, self.scalers, self.avg_d))
         else:
-            agg = pna_aggregate(hp, csr, self.aggregators, self.scalers, self.avg_d, zero_isolated=True)
+            agg = pna_aggregate(hp, csr, self.aggregators, self.scalers, self.avg_d, zero_isolated=True, relu_var=True)
             h = self.posttrans(agg, first_weight=w0)
         if self.batch_norm:
             h = self.batchnorm_h(h)

@@ -11,7 +11,7 @@ from typing import Optional
 
 import torch
 
-from .csr import CSRGraph, build_csr
+from .csr import CSRGraph, build_csr, tensor_version
 
 _ATTR = "_pna_b200_csr"
 
@@ -60,13 +60,21 @@ def graph_num_nodes(g) -> int:
 
 def graph_csr(g, device: torch.device) -> CSRGraph:
     """CSR of the graph on `device`, built on first use and cached on the object."""
-    csr = getattr(g, _ATTR, None)
-    if csr is not None and csr.device == device:
-        return csr
     src, dst = graph_edges(g)
-    csr = build_csr(src.to(device), dst.to(device), graph_num_nodes(g))
+    n = graph_num_nodes(g)
+    # a graph mutated in place (add_edges / remove_edges / add_self_loop) hands out different edge tensors or counts:
+    # the stamp of what the cached CSR was built from is compared on every call
+    # (foreign graph types such as dgl.DGLGraph materialise fresh edge tensors on every edges() call, so only the counts
+    # are comparable there; this package's Graph also stamps the tensors' identity and in-place version)
+    stamp = (n, int(src.numel()))
+    if isinstance(g, Graph):
+        stamp += (src.data_ptr(), dst.data_ptr(), tensor_version(src), tensor_version(dst))
+    hit = getattr(g, _ATTR, None)
+    if hit is not None and hit[0] == stamp and hit[1].device == device:
+        return hit[1]
+    csr = build_csr(src.to(device), dst.to(device), n)
     try:
-        setattr(g, _ATTR, csr)
+        setattr(g, _ATTR, (stamp, csr, src, dst))     # the tensors are kept so their storage cannot be recycled
     except Exception:
         pass
     return csr

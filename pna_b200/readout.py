@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 from .aggregate import pna_aggregate
-from .csr import CSRGraph, build_csr
+from .csr import CSRGraph, build_csr, tensor_version
 
 _UNIT = {"log": 1.0, "lin": 1.0}        # identity scaler only: the averages are never read
 _CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
@@ -22,7 +22,7 @@ _CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 
 def batch_csr(batch: torch.Tensor, n_graphs: int) -> CSRGraph:
     """CSR whose row g lists the nodes of graph g; cached on the identity of ``batch`` (one per mini-batch)."""
-    key = (batch.data_ptr(), batch._version, int(batch.numel()), int(n_graphs), str(batch.device))
+    key = (batch.data_ptr(), tensor_version(batch), int(batch.numel()), int(n_graphs), str(batch.device))
     hit = _CACHE.get(key)
     if hit is not None:
         _CACHE.move_to_end(key)

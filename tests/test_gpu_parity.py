@@ -423,8 +423,10 @@ def _graph(P, g):
     return P.Graph(ei[0], ei[1], g["h"].size(0)).to(dev())
 
 
-def test_golden_dgl_simple_layer(P):
-    g = load_golden("dgl_simple")
+@pytest.mark.parametrize("name", ["dgl_simple", "dgl_simple_var"])
+def test_golden_dgl_simple_layer(P, name):
+    """dgl_simple_var: "var" over identical neighbour rows -- the DGL flavour clamps it at 0 (PNA_FLAG_RELU_VAR)."""
+    g = load_golden(name)
     lay = P.PNASimpleLayer(aggregators=g["aggregators"], scalers=g["scalers"], avg_d=g["avg_d"], **g["ctor"])
     lay.load_state_dict(g["state_dict"])
     lay = lay.to(dev()).eval()
@@ -448,10 +450,13 @@ def test_golden_dgl_layer(P, name):
     torch.testing.assert_close(out, g["out"], **LAYER_TOL)
 
 
-def test_golden_dense_layer(P):
-    """The dense reference layer (imports unmodified here) on a generated graph, including its max/min axis quirk."""
-    g = load_golden("dense_k1_k2")
-    lay = P.dense.PNALayer(aggregators=A4, scalers=S3, avg_d=g["avg_d"], **g["ctor"])
+@pytest.mark.parametrize("name", ["dense_k1_k2", "dense_self_loop", "dense_directed"])
+def test_golden_dense_layer(P, name):
+    """The dense reference layer (imports unmodified here) on a generated graph, including its max/min axis quirk.
+    dense_self_loop / dense_directed: a DIRECTED adjacency (row degree != column degree), "var" among the aggregators,
+    with and without self_loop -- the scalers must see D = adj.sum(-1) of the loop-free adjacency in every block."""
+    g = load_golden(name)
+    lay = P.dense.PNALayer(aggregators=g.get("aggregators", A4), scalers=g.get("scalers", S3), avg_d=g["avg_d"], **g["ctor"])
     lay.load_state_dict(g["state_dict"])
     lay = lay.to(dev()).eval()
     with torch.no_grad():

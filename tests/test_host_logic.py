@@ -104,3 +104,15 @@ def test_padding_algebra_is_exact_on_the_oracle():
     assert p.shape == (n, 3 * fp) and torch.equal(p.view(n, 3, fp)[:, :, :f], xt.view(n, 3, f)) and float(p.view(n, 3, fp)[:, :, f:].abs().sum()) == 0
     Wr = pad.expand_weight_rows(torch.randn(f, 9), f, fp)
     assert Wr.shape == (fp, 9) and float(Wr[f:].abs().sum()) == 0
+
+
+def test_cache_keys_accept_inference_mode_tensors():
+    """Tensors created under torch.inference_mode() do not track a version counter; the cache keys must not read it."""
+    from pna_b200.csr import tensor_version
+    with torch.inference_mode():
+        t = torch.arange(6).view(2, 3)
+    assert t.is_inference() and tensor_version(t) is None
+    u = torch.arange(6)
+    v0 = tensor_version(u)
+    u.add_(1)
+    assert tensor_version(u) == v0 + 1

@@ -49,14 +49,21 @@ def test_conv_layer_forward(name):
     assert torch.equal(out, g["out"])
 
 
-def test_dgl_reduce_matches_reference_mailbox_reduce():
-    g = load_golden("dgl_simple")
+@pytest.mark.parametrize("name", ["dgl_simple", "dgl_simple_var"])
+def test_dgl_reduce_matches_reference_mailbox_reduce(name):
+    g = load_golden(name)
     ei = g["edge_index"]
     agg = O.dgl_reduce(g["h"][ei[0]], None, ei[1], g["h"].size(0), g["aggregators"].split(), g["scalers"].split(), g["avg_d"])
     assert torch.equal(agg, g["aggregate"])
     # in-degree-0 rows are all zero in the DGL flavour, std columns included
     iso = torch.bincount(ei[1], minlength=g["h"].size(0)) == 0
     assert iso.any() and agg[iso].abs().max() == 0
+    if "var" in g["aggregators"].split():
+        # relu(var) (models/dgl/aggregators.py:22-26): identical neighbour rows give exact zeros, never a negative value
+        A = g["aggregators"].split()
+        f = g["h"].size(1)
+        var_block = agg[:, A.index("var") * f:(A.index("var") + 1) * f]
+        assert var_block.min() >= 0 and (var_block[~iso] == 0).any()
 
 
 def test_dgl_vs_pyg_flavours_differ_only_on_isolated_rows():
