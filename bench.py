@@ -10,10 +10,15 @@ A "step" is one pass of the hot path over the whole graph: CSR (resident, built 
   e2e          edges/s of PNAConvSimple.forward(x, edge_index) called with pinned HOST tensors: H2D of x and
                edge_index, CSR build, aggregation, post-MLP, D2H of the layer output, all inside the timed region
   roofline     B_min / step time against MEASURED_PEAKS.json's HBM copy bandwidth
+  parity       the step's output compared with the CPU oracle inside this run (every row at N = 1), asserted
+  configs      (N = 1) the other BASELINE.json shapes that fit one GPU -- configs[0], [2], one GPU's share of [3] and [4] --
+               each with its step time, B_min fraction and in-run parity; configs[0] also times the reference's CPU PNAConv
   cpu_baseline the reference's PyTorch CPU op sequence (oracle/pna_oracle.py, a port: torch_geometric/torch_scatter
                are not installable) timed on the host cores of this box on the same graph
 N = 1: BASELINE.json configs[1] (ogbn-arxiv-shaped, 169 343 nodes / 1 166 243 edges, F = 128, fp32).
-N > 1: weak scaling -- a graph N times larger, destination-partitioned, one halo all-to-all per step (pna_b200/dist.py).
+N > 1: bench_multi.py -- configs[3] at N = 4 (graph-batch shard), configs[4] at N = 8 (destination partition + halo exchange),
+       configs[4] at N/8 scale otherwise.
+--impl reference: the same workload's reference op sequence on the host cores (rank 0 only), same config / steps / warm-up.
 """
 from __future__ import annotations
 
@@ -21,9 +26,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import threading
 import time
 
 import torch
@@ -32,107 +35,66 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-AGGRS = ["mean", "max", "min", "std"]
-SCALERS = ["identity", "amplification", "attenuation"]
-METRIC = "aggregated edges/sec (PNA layer fwd)"
-UNIT = "edges/s"
-FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+import bench_common as bc                                   # noqa: E402
+from bench_common import AGGRS, SCALERS, METRIC, UNIT        # noqa: E402
 
 
-def measured_peaks():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured"
-        except Exception:
-            pass
-    return FALLBACK_HBM_GBS, "fallback"
+def config2_dict(n, e, f, max_deg):
+    """Printed identically by both arms."""
+    return {"workload": "ogbn-arxiv-shaped CSR (BASELINE.json configs[1])", "n_nodes": n, "n_edges": e, "n_feat": f,
+            "aggregators": AGGRS, "scalers": SCALERS, "dst_skew": "perm[floor(N*u^3)]", "max_in_degree": max_deg,
+            "l2": bc.L2_NOTE, "parallelism": "1 gpu"}
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
-
-    def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-        return self
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-
-    def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for nm, v in zip(names, r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
-
-
-def make_workload(world: int, rank: int):
-    """config 2 for this rank.  N = 1: the graph itself.  N > 1: see pna_b200/dist.py (weak scaling)."""
-    from pna_b200 import synth
-    ei, x = synth.arxiv_like(n_feat=128, seed=0)
-    return ei, x
-
-
-def cpu_reference_layer(ei, x, deg_hist, steps: int, warmup: int):
-    """The reference's CPU path for PNAConvSimple.forward (port: oracle/pna_oracle.py) on the host cores of this box.
-
-    torch's CPU scatter/index kernels do not scale to 100+ threads (oversubscription makes them slower), so a few
-    thread counts are tried in the warm-up and the FASTEST one is timed and reported -- the baseline gets every
-    advantage the hardware offers."""
-    from oracle import pna_oracle as O
-    f = x.size(1)
-    torch.manual_seed(0)
-    lay = O.PNAConvSimpleOracle(f, f, AGGRS, SCALERS, deg_hist)
+def best_thread_count(fn):
+    """torch's CPU scatter/index kernels do not scale to 100+ threads (oversubscription makes them slower): a few thread
+    counts are tried and the FASTEST is used -- the baseline gets every advantage the hardware offers."""
     ncpu = os.cpu_count() or 1
     candidates = sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True)
     best_t, best_n = None, ncpu
-    with torch.no_grad():
-        for n in candidates:
-            torch.set_num_threads(n)
-            lay(x, ei)                                  # warm this setting
-            t0 = time.perf_counter()
-            lay(x, ei)
-            dt = time.perf_counter() - t0
-            if best_t is None or dt < best_t:
-                best_t, best_n = dt, n
-        torch.set_num_threads(best_n)
-        times = []
-        for i in range(max(0, warmup - 1) + steps):
-            t0 = time.perf_counter()
-            lay(x, ei)
-            dt = time.perf_counter() - t0
-            if i >= max(0, warmup - 1):
-                times.append(dt)
-    return times, best_n, {"threads_tried": candidates, "host_cpus": ncpu}
+    for n in candidates:
+        torch.set_num_threads(n)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best_t, best_n = dt, n
+    torch.set_num_threads(best_n)
+    return best_n, {"threads_tried": candidates, "host_cpus": ncpu}
+
+
+def cpu_time(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+# ---- --impl reference ----------------------------------------------------------------------------------------------------
+def reference_workload(world: int):
+    """(edge_index, x, config dict, sample note) of the reference arm: the workload of the repo arm at this N, bounded so
+    that one CPU pass takes about a second (N = 1: the full config-2 graph)."""
+    from pna_b200 import synth
+    import bench_multi
+    if world == 1:
+        ei, x = synth.arxiv_like(n_feat=128, seed=0)
+        md = int(torch.bincount(ei[1], minlength=x.size(0)).max())
+        return ei, x, config2_dict(x.size(0), ei.size(1), 128, md), 1.0, "full config-2 graph"
+    cfg = bench_multi.config_dict(world)
+    if bench_multi.workload_for(world) == "config4":
+        ei = synth.superpixel_shard(0, 2500, "cpu")
+        x = synth.hash_features(torch.arange(2500 * 70), 64)
+        return ei, x, cfg, 2500 * 70 * 8 / cfg["n_edges"], "2 500 of the 60 000 superpixel graphs (175 000 nodes / 1.4 M edges, F=64)"
+    n, e, f = 156_250, 1_562_500, cfg["n_feat"]
+    src, dst = next(iter(synth.powerlaw_stream(n, e, "cpu", seed=0, chunk=e)))
+    x = synth.hash_features(torch.arange(n), f)
+    return torch.stack([src, dst]), x, cfg, e / cfg["n_edges"], \
+        f"a 1/{cfg['n_edges'] // e} scale instance of the power-law generator (156 250 nodes / 1 562 500 edges, F={f})"
 
 
 def run_reference(args):
@@ -141,34 +103,137 @@ def run_reference(args):
     if rank != 0:
         return
     from pna_b200 import synth
-    ei, x = make_workload(1, 0)
-    n, e = x.size(0), ei.size(1)
+    from oracle import pna_oracle as O
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    world = max(world, args.gpus)
+    ei, x, cfg, frac, sample = reference_workload(world)
+    n, e, f = x.size(0), ei.size(1), x.size(1)
     deg = synth.degree_histogram(ei[1], n)
-    times, threads, info = cpu_reference_layer(ei, x, deg, args.steps, max(1, min(args.warmup, 2)))
-    total = sum(times)
-    v = e * len(times) / total
+    avg = O.avg_deg_from_histogram(deg)
+    torch.manual_seed(0)
+    lay = O.PNAConvSimpleOracle(f, f, AGGRS, SCALERS, deg)
+    with torch.no_grad():
+        threads, info = best_thread_count(lambda: O.simple_propagate(x, ei, AGGRS, SCALERS, avg))
+        ts = cpu_time(lambda: O.simple_propagate(x, ei, AGGRS, SCALERS, avg), args.steps, args.warmup)
+        tl = cpu_time(lambda: lay(x, ei), max(2, min(args.steps, 5)), 1)
+    v = e * len(ts) / sum(ts)
+    v_layer = e * len(tl) / sum(tl)
+    what = ("the reference's aggregation op sequence (index_select, 6x scatter_add, amin, amax, degree, 3 scalers, cats: "
+            "models/pytorch_geometric/pna.py:242-249, aggregators.py, scalers.py restated in oracle/pna_oracle.py) in torch CPU")
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ogbn-arxiv-shaped CSR (configs[1])", "n_nodes": n, "n_edges": e, "n_feat": x.size(1),
-                   "layer": "PNAConvSimple(128,128) forward: aggregate + post-MLP"},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts), "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", **info,
-                         "sample": f"full config-2 graph, {len(times)} forward passes of the reference op sequence "
-                                   "(index_select, 6x scatter_add, amin, amax, degree, 3 scalers, cats, Linear) in torch CPU"},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                         "sample": f"{sample}: {len(ts)} passes of {what}", "sample_fraction_of_workload": frac},
+        "e2e": {"value": v_layer, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "what": "PNAConvSimple.forward (aggregation + post-MLP Linear) on the same sample, torch CPU"},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+# ---- the other single-GPU shapes (N = 1 `configs`) ------------------------------------------------------------------------
+def side_configs(dev, flush, steps, peak):
+    import pna_b200
+    from pna_b200 import synth
+    from oracle import pna_oracle as O
+    res = {}
+
+    def measure(name, src, dst, x, features_of, note, n_sample, extra=None):
+        n, f = x.shape
+        e = int(src.numel())
+        deg_hist = torch.bincount(torch.bincount(dst, minlength=n)).cpu()
+        avg = pna_b200.avg_deg_from_histogram(deg_hist)
+        csr = pna_b200.build_csr(src.to(dev), dst.to(dev), n)
+        xd = x.to(dev)
+        out = torch.empty((n, 12 * f), dtype=x.dtype, device=dev)
+        ts = bc.timed_steps(lambda: pna_b200.aggregate_forward(xd, csr, AGGRS, SCALERS, avg, out=out), steps, 3, flush)
+        ms = sum(ts) / len(ts)
+        par = bc.sampled_parity(out, csr.rowptr, csr.col, features_of, avg, csr.split_threshold, n_rows_sample=n_sample,
+                                max_edges=4_000_000, rows=_rows_with_hubs(csr, n_sample))
+        by = synth.algorithmic_bytes(n, e, f, x.element_size(), 12 * f)
+        rec = {"workload": note, "n_nodes": n, "n_edges": e, "n_feat": f, "dtype": str(x.dtype).replace("torch.", ""), "ms_per_step": ms,
+               "edges_per_s": e / (ms * 1e-3), "b_min_bytes": by["b_min"], "frac_of_measured_hbm_peak": by["b_min"] / (ms * 1e-3) / 1e9 / peak,
+               "split_rows": csr.n_hubs, "max_in_degree": csr.max_degree, "parity_ok": par["ok"],
+               "parity_max_err": max(par["max_err_light"], par["max_err_split_vs_f64"]), "parity_rows": par["rows"] + par["big_rows"],
+               "parity_rows_are_all_rows": par["rows"] + par["big_rows"] == n}
+        if extra:
+            rec.update(extra(csr, xd, avg, deg_hist))
+        res[name] = rec
+        assert par["ok"], f"parity failed on {name}: {par}"
+        del out, xd, csr
+        torch.cuda.empty_cache()
+
+    # configs[0]: 64 x 1k-node graphs, F = 16; plus the reference's own CPU PNAConv(16,16,towers=4,divide_input=True) timing
+    ei, x = synth.multitask_like()
+
+    def config1_layer(csr, xd, avg, deg_hist):
+        torch.manual_seed(0)
+        ref = O.PNAConvOracle(16, 16, AGGRS, SCALERS, deg_hist, towers=4, divide_input=True)
+        lay = pna_b200.PNAConv(16, 16, AGGRS, SCALERS, deg_hist, towers=4, divide_input=True)
+        lay.load_state_dict(ref.state_dict())
+        lay = lay.to(dev)
+        eid = ei.to(dev)
+        with torch.no_grad():
+            threads, info = best_thread_count(lambda: ref(x, ei))
+            tc = cpu_time(lambda: ref(x, ei), 3, 1)
+            want = ref(x, ei)
+            got = lay(xd, eid, csr=csr)
+            for _ in range(3):
+                lay(xd, eid, csr=csr)
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(20):
+                lay(xd, eid, csr=csr)
+            t.record(); torch.cuda.synchronize()
+        err = float((got.cpu() - want).abs().max())
+        cpu_ms = 1e3 * sum(tc) / len(tc)
+        gpu_ms = s.elapsed_time(t) / 20
+        return {"layer": "PNAConv(16, 16, towers=4, divide_input=True) forward (multitask_benchmark/README.md:36)",
+                "cpu_reference": {"ms": cpu_ms, "edges_per_s": ei.size(1) / (cpu_ms * 1e-3), "cores": threads, "kind": "port", **info,
+                                  "what": "the reference's PNAConv op sequence (oracle/pna_oracle.py PNAConvOracle) in torch CPU, 3 passes"},
+                "gpu_layer": {"ms": gpu_ms, "edges_per_s": ei.size(1) / (gpu_ms * 1e-3), "max_abs_err_vs_cpu_reference": err}}
+    measure("configs[0]", ei[0], ei[1], x, lambda idx: x[idx], "multitask-shaped batch: 64 x 1 000-node random graphs, F=16 fp32",
+            64_000, config1_layer)
+
+    # configs[2]: ZINC-shaped batch, F = 75 bf16 (unpadded 150-byte rows)
+    ei, x, _ = synth.zinc_like(dtype=torch.bfloat16)
+    measure("configs[2]", ei[0], ei[1], x, lambda idx: x[idx], "ZINC-shaped batch: 12 000 molecule-like graphs, F=75 bf16 (150-byte rows)",
+            x.size(0))
+
+    # configs[3], one GPU's share: 15 000 superpixel graphs, F = 64
+    ei = synth.superpixel_shard(0, 15_000, dev)
+    n4 = 15_000 * 70
+    x4 = synth.hash_features(torch.arange(n4, device=dev), 64)
+    measure("configs[3] (one GPU's share)", ei[0], ei[1], x4, lambda idx: synth.hash_features(idx, 64),
+            "15 000 of the 60 000 superpixel kNN graphs (70 nodes, k=8), F=64 fp32", 120_000)
+    del x4
+
+    # configs[4], one GPU's share: power-law 1.25 M / 12.5 M, F = 256
+    src, dst = next(iter(synth.powerlaw_stream(1_250_000, 12_500_000, dev, seed=0)))
+    x5 = synth.hash_features(torch.arange(1_250_000, device=dev), 256)
+    measure("configs[4] (one GPU's share)", src, dst, x5, lambda idx: synth.hash_features(idx, 256),
+            "power-law 1.25 M nodes / 12.5 M edges (Zipf 1.5 sources and destinations), F=256 fp32", 100_000)
+    return res
+
+
+def _rows_with_hubs(csr, n_sample):
+    g = torch.Generator().manual_seed(11)
+    rows = torch.randperm(csr.n_nodes, generator=g)[: min(n_sample, csr.n_nodes)]
+    if csr.n_hubs and n_sample < csr.n_nodes:
+        info = csr.hub_info.cpu().long()
+        rows = torch.unique(torch.cat([rows, info[torch.argsort(info[:, 3], descending=True)[:16], 0]]))
+    return rows
+
+
+# ---- the repo arm at N = 1 ----------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
     import pna_b200
     from pna_b200 import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
@@ -177,10 +242,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        from pna_b200 import dist as pdist
-        return pdist.bench_multi_gpu(args, METRIC, UNIT, AGGRS, SCALERS, measured_peaks, ClockSampler)
+        import bench_multi
+        return bench_multi.run(args)
 
-    ei, x = make_workload(1, 0)
+    ei, x = synth.arxiv_like(n_feat=128, seed=0)
     n, e, f = x.size(0), ei.size(1), x.size(1)
     deg_hist = synth.degree_histogram(ei[1], n)
     avg_deg = pna_b200.avg_deg_from_histogram(deg_hist)
@@ -201,41 +266,20 @@ def run_ours(args):
     csr_ms = ev[0].elapsed_time(ev[1]) / 5
 
     out = torch.empty((n, 12 * f), dtype=torch.float32, device=dev)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    flush_rd = torch.zeros(128 << 20, dtype=torch.float32, device=dev)   # 512 MiB, read after the write (see l2_flush)
-
-    def l2_flush():
-        """Evict everything of the previous iteration: write 512 MiB, then READ another 512 MiB so the L2 is left full of
-        CLEAN lines -- a write-only flush leaves ~126 MB of dirty lines whose write-back would be charged to the timed step."""
-        flush.zero_()
-        flush_rd.sum()
+    flush = bc.L2Flush(dev)
 
     def step(**kw):
         pna_b200.aggregate_forward(xd, csr, AGGRS, SCALERS, avg_deg, out=out, **kw)
 
-    def timed(k, warm, **kw):
-        for _ in range(warm):
-            l2_flush(); step(**kw)
-        starts = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
-        ends = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
-        torch.cuda.synchronize()
-        for i in range(k):
-            l2_flush()                         # evict x / CSR / out lines of the previous iteration from L2
-            starts[i].record()
-            step(**kw)
-            ends[i].record()
-        torch.cuda.synchronize()
-        return [s.elapsed_time(t) for s, t in zip(starts, ends)]
-
     # clocks / throttle reasons are sampled (20 Hz) while the GPU runs this workload: the timed steps themselves last
     # only ~15 ms, so the sampler brackets them with extra untimed passes of the same kernels to collect enough samples
-    with ClockSampler(local) as clk:
+    with bc.ClockSampler(local) as clk:
         time.sleep(0.06)
         t_end = time.perf_counter() + 0.5
         while time.perf_counter() < t_end:
             step()
         torch.cuda.synchronize()
-        per_step = timed(args.steps, args.warmup)
+        per_step = bc.timed_steps(step, args.steps, args.warmup, flush)
         t_end = time.perf_counter() + 0.5
         while time.perf_counter() < t_end:
             step()
@@ -244,12 +288,15 @@ def run_ours(args):
     t_ms = sum(per_step) / len(per_step)
     value = e / (t_ms * 1e-3)
     from pna_b200.aggregate import fold_finalize_enabled
-    # k_rows_stream (+ k_hub_finalize when rows were split and the finalize is not folded into the stream kernel)
     launches_per_step = 1 + (1 if (csr.n_hubs and not fold_finalize_enabled()) else 0)
-    # (the e2e / layer_fwd legs additionally launch k_split_weight + k_linear_3xtf32 and the CSR-build kernels)
+
+    # in-run parity: EVERY row of the step's output against the CPU oracle
+    par = bc.sampled_parity(out, csr.rowptr, csr.col, lambda idx: x[idx], avg_deg, csr.split_threshold, n_rows_sample=n,
+                            max_edges=1 << 40, rows=torch.arange(n))
+    assert par["ok"], f"parity failed: {par}"
 
     bytes_ = synth.algorithmic_bytes(n, e, f, 4, 12 * f)
-    peak, peak_src = measured_peaks()
+    peak, peak_src = bc.measured_peaks()
     achieved = bytes_["b_min"] / (t_ms * 1e-3) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -262,8 +309,9 @@ def run_ours(args):
     # e2e: the public layer call with HOST buffers (pinned), copies inside the timed region
     torch.manual_seed(0)
     lay = pna_b200.PNAConvSimple(f, f, AGGRS, SCALERS, deg_hist).to(dev)
-    xh, eih = x.pin_memory(), ei.pin_memory()
+    xh = x.pin_memory()
     outh = torch.empty((n, f), dtype=torch.float32).pin_memory()
+    eih_steps = [ei.clone().pin_memory() for _ in range(4)]    # distinct host tensors: the device copy is always fresh
 
     def e2e_step():
         # the public host-buffer call: pinned x / edge_index in, pinned result out; a new edge_index object every step,
@@ -271,7 +319,6 @@ def run_ours(args):
         lay.forward_host(xh, eih_steps[e2e_step.i % len(eih_steps)], out=outh)
         e2e_step.i += 1
     e2e_step.i = 0
-    eih_steps = [ei.clone().pin_memory() for _ in range(4)]    # distinct host tensors: the device copy is always fresh
 
     # PCIe health of this box (context for e2e: the layer call moves 192 MB per step over PCIe)
     def copy_rate(fn, nbytes):
@@ -298,6 +345,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_wall_ms = 1e3 * (time.perf_counter() - t0) / k2
     e2e_ms = max(s2.elapsed_time(e2) / k2, e2e_wall_ms)      # host-side launch/sync time counts too
+
     def layer_ms():
         with torch.no_grad():
             s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -316,23 +364,33 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        times, threads, info = cpu_reference_layer(ei, x, deg_hist, 3, 1)
-        cpu = {"value": e * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": "port", **info,
-               "sample": "full config-2 graph, 3 forward passes of PNAConvSimple's reference op sequence in torch CPU "
-                         "(oracle/pna_oracle.py; torch_geometric/torch_scatter not installable)"}
+        from oracle import pna_oracle as O
+        with torch.no_grad():
+            threads, info = best_thread_count(lambda: O.simple_propagate(x, ei, AGGRS, SCALERS, avg_deg))
+            tc = cpu_time(lambda: O.simple_propagate(x, ei, AGGRS, SCALERS, avg_deg), 3, 1)
+        cpu = {"value": e * len(tc) / sum(tc), "unit": UNIT, "cores": threads, "kind": "port", **info,
+               "sample": "full config-2 graph, 3 passes of the reference's aggregation op sequence (models/pytorch_geometric/pna.py:"
+                         "242-249 restated in oracle/pna_oracle.py; torch_geometric/torch_scatter not installable) in torch CPU"}
+
+    sides = None
+    if not args.no_side_configs:
+        del out
+        torch.cuda.empty_cache()
+        sides = side_configs(dev, flush, max(5, min(args.steps, 20)), peak)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": "ogbn-arxiv-shaped CSR (BASELINE.json configs[1])", "n_nodes": n, "n_edges": e, "n_feat": f,
-                   "aggregators": AGGRS, "scalers": SCALERS, "dst_skew": "perm[floor(N*u^3)]", "max_in_degree": csr.max_degree,
-                   "split_rows": csr.n_hubs, "l2": "flushed between timed steps (512 MiB written, then 512 MiB read so no dirty lines remain)", "parallelism": "1 gpu"},
+        "data": "synthetic", "config": config2_dict(n, e, f, csr.max_degree),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_model": "B_min = N*F*s + 4E + 4(N+1) + 12*N*F*s",
                      "b_min_bytes": bytes_["b_min"], "b_gather_bytes": bytes_["b_gather"],
                      "effective_gbs_b_gather": bytes_["b_gather"] / (t_ms * 1e-3) / 1e9},
-        "kernels_ms": {"step_min": min(per_step), "step_median": statistics.median(per_step),
+        "parity": {"ok": par["ok"], "parity_max_err": max(par["max_err_light"], par["max_err_split_vs_f64"]),
+                   "max_err_light_rows": par["max_err_light"], "max_err_split_rows_vs_f64": par["max_err_split_vs_f64"],
+                   "rows_checked": par["rows"] + par["big_rows"], "split_rows_checked": par["split_rows"] + par["big_rows"],
+                   "what": "every row of the timed step's output vs the CPU oracle (fp32 op sequence; rows split across warps vs float64)"},
+        "kernels_ms": {"step_min": min(per_step), "step_median": statistics.median(per_step), "split_rows": csr.n_hubs,
                        "kernels": ("k_rows_stream (rows + chunks of split rows, split rows finalized by the last-arriving warp)"
                                    if fold_finalize_enabled() else "k_rows_stream (rows + chunks of split rows) + k_hub_finalize")
                                   + "; per-kernel times: profiles/"},
@@ -350,6 +408,7 @@ def run_ours(args):
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "cpu_baseline": cpu,
+        "configs": sides,
     }
     print(json.dumps(line))
 
@@ -361,6 +420,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip the `configs` sub-object (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -230,6 +230,24 @@ int pna_aggregate_bwd(const pna_agg_t* desc, const void* grad_out, int64_t ld_gr
 int pna_gather_rows(const void* src, int64_t ld_src, const int32_t* idx, int64_t n_idx, void* dst, int64_t ld_dst,
                     int32_t n_feat, int32_t dtype, pna_stream_t stream);
 
+/* ---- the same exchange as ONE kernel of peer loads (no pack, no collective, no unpack) -------------------------------
+ * Every rank's feature rows live in a buffer that is mapped into every process (symmetric memory / CUDA IPC over NVLink).
+ * peer_rows: DEVICE array of n_ranks base pointers of those buffers (row pitch ld_rows elements on every rank);
+ * enc[i] = owner << peer_shift | row-on-owner names the i-th de-duplicated remote source row this rank needs;
+ * dst[i, :] (pitch ld_dst; normally the tail of the rank's [local ; halo] buffer) receives it.  One remote row crosses
+ * NVLink once per layer however many local destinations gather it afterwards. */
+int pna_halo_pull(const void* const* peer_rows, int64_t ld_rows, const int32_t* enc, int32_t peer_shift, int64_t n_idx, void* dst,
+                  int64_t ld_dst, int32_t n_feat, int32_t dtype, pna_stream_t stream);
+
+/* Device-side barrier between the ranks of one box, enqueued on `stream`: peer_flags is a DEVICE array of n_ranks pointers to
+ * each rank's uint64 flags[n_ranks] (zero-initialised once, mapped into every process like the feature rows).  Rank r
+ * stores `epoch` into flags[r] of every peer and waits until its own flags all reach `epoch`; epochs must increase by
+ * one per call on every rank.  Orders "every rank has written its feature rows" before the pulls / peer gathers of the
+ * next kernel.  If a peer does not arrive within timeout_ns (0 = 2 s) the kernel gives up and sets *status = 1 (DEVICE int,
+ * nullable) instead of hanging the GPU. */
+int pna_peer_barrier(const void* const* peer_flags, int32_t rank, int32_t world, uint64_t epoch, uint64_t timeout_ns,
+                     int32_t* status, pna_stream_t stream);
+
 /* ---- first dense linear of the post-aggregation MLP on the tensor cores (north_star: "the post-MLP uses tensor
  * cores only for its dense linear"; reference pna.py:222-227 post_nn[0], models/dgl/pna_layer.py:31 posttrans) -----
  * y[n_rows, n_out] = a[n_rows, n_in] . weight[n_out, n_in]^T + bias, fp32 in / fp32 out, fp32-accurate: every operand

@@ -16,7 +16,7 @@ REPO_ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("PNA_B200_LIB") or os.path.join(_HERE, "libpna_sm100.so")   # env override: tuning builds only
 CUDA_SOURCES = [os.path.join(_HERE, "csrc", n) for n in
                 ("pna_aggregate.cu", "pna_aggregate_f32_vec.cu", "pna_aggregate_f32_scalar.cu", "pna_aggregate_bf16_vec.cu",
-                 "pna_aggregate_bf16_scalar.cu", "pna_aggregate_f32_fsplit.cu", "pna_aggregate_bwd.cu", "pna_linear.cu", "pna_csr.cu", "pna_misc.cu")]
+                 "pna_aggregate_bf16_scalar.cu", "pna_aggregate_f32_fsplit.cu", "pna_aggregate_bwd.cu", "pna_linear.cu", "pna_csr.cu", "pna_peer.cu", "pna_misc.cu")]
 CUDA_HEADERS = [os.path.join(_HERE, "csrc", n) for n in ("common.cuh", "pna_aggregate.cuh", "pna_aggregate_impl.cuh")] + [
     os.path.join(REPO_ROOT, "include", "pna_b200.h")]
 BUILD_DIR = os.path.join(_HERE, "csrc", "build")
@@ -38,7 +38,7 @@ FLAG_ZERO_ISOLATED, FLAG_SKIP_LIGHT, FLAG_SKIP_HUBS, FLAG_RELU_VAR = 1, 2, 4, 8
 
 # every symbol the header declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = ("pna_csr_workspace_bytes", "pna_csr_build", "pna_csr_light_view", "pna_csr_light_view_workspace_bytes", "pna_aggregate_fwd", "pna_aggregate_bwd",
-                    "pna_gather_rows", "pna_linear_fwd", "pna_linear_scaled_fwd", "pna_row_scales", "pna_linear_workspace_bytes", "pna_query", "pna_last_error")
+                    "pna_gather_rows", "pna_halo_pull", "pna_peer_barrier", "pna_linear_fwd", "pna_linear_scaled_fwd", "pna_row_scales", "pna_linear_workspace_bytes", "pna_query", "pna_last_error")
 
 
 class PnaError(RuntimeError):
@@ -161,6 +161,11 @@ def lib() -> C.CDLL:
         L.pna_gather_rows.restype = C.c_int
         L.pna_gather_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_int32, C.c_void_p]
+        L.pna_halo_pull.restype = C.c_int
+        L.pna_halo_pull.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                    C.c_int32, C.c_void_p]
+        L.pna_peer_barrier.restype = C.c_int
+        L.pna_peer_barrier.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
         L.pna_linear_workspace_bytes.restype = C.c_int
         L.pna_linear_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
         L.pna_linear_fwd.restype = C.c_int

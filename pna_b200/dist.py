@@ -167,6 +167,129 @@ class HaloAggregator:
         return aggregate_forward(self.x_ext, self.csr, aggregators, scalers, avg_deg, out=out, view=self.view_boundary, **kw)
 
 
+@dataclass
+class PullPlan:
+    """What one rank needs for the pull plane: computed locally from the rank's own in-edges, no id exchange at all
+    (the puller names the rows; the owners do nothing)."""
+    rank: int
+    world: int
+    lo: int
+    hi: int
+    n_local: int
+    n_halo: int
+    shift: int
+    src_ext: torch.Tensor          # int64 [E_r] sources remapped to [0, n_local + n_halo)
+    dst_local: torch.Tensor        # int64 [E_r]
+    halo_ids: torch.Tensor         # int64 [n_halo] global ids of the de-duplicated remote sources, sorted (grouped by owner)
+    enc: torch.Tensor              # int32 [n_halo] owner << shift | row-on-owner
+    n_remote_edges: int
+
+
+def build_pull_plan(src_global: torch.Tensor, dst_global: torch.Tensor, bounds: torch.Tensor, rank: int, world: int) -> PullPlan:
+    dev = src_global.device
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    n_local = hi - lo
+    if src_global.numel() and (int(dst_global.min()) < lo or int(dst_global.max()) >= hi):
+        raise ValueError("build_pull_plan: an edge's destination is outside this rank's range")
+    remote = (src_global < lo) | (src_global >= hi)
+    halo_ids = torch.unique(src_global[remote])
+    n_halo = int(halo_ids.numel())
+    pos = torch.searchsorted(halo_ids, src_global) if n_halo else torch.zeros_like(src_global)
+    src_ext = torch.where(remote, n_local + pos, src_global - lo)
+    shift = peer_shift_for(bounds)
+    enc = encode_peer_sources(halo_ids, bounds, shift).to(torch.int32) if n_halo else torch.zeros(0, dtype=torch.int32, device=dev)
+    return PullPlan(rank, world, lo, hi, n_local, n_halo, shift, src_ext, dst_global - lo, halo_ids, enc, int(remote.sum()))
+
+
+class PullAggregator:
+    """[local ; halo] source buffer whose halo tail is filled by ONE kernel of peer loads (``pna_halo_pull``): the
+    all-to-all of the north star without a collective -- no id exchange when the graph is planned, no pack kernel, no
+    send buffer, no NCCL call per layer; a remote row crosses NVLink once per layer however often it is gathered.
+
+    Protocol (one layer): every rank writes its rows into ``x_local`` -> ``exchange()`` = device-side barrier
+    (``pna_peer_barrier``: one flag store per peer, spin on the own flags) + the pull -> aggregation from the local
+    buffer.  The feature buffer is DOUBLE-BUFFERED (``flip()`` between layers / steps): a rank may already be writing
+    layer l+1's rows while slower peers still pull layer l's, and the barrier of layer l+1 separates layer l's pulls
+    from the writes of layer l+2 into the same buffer.
+    """
+
+    def __init__(self, plan: PullPlan, n_feat: int, dtype=torch.float32, group=None, buffers: int = 2, _alloc=None):
+        dev = plan.src_ext.device
+        self.plan, self.group, self.n_feat, self.dtype = plan, group, n_feat, dtype
+        self.csr = build_csr(plan.src_ext, plan.dst_local, plan.n_local, n_src=plan.n_local + max(plan.n_halo, 0))
+        rows = torch.tensor([plan.n_local + plan.n_halo], dtype=torch.int64, device=dev)
+        if _alloc is None and plan.world > 1:
+            dist.all_reduce(rows, op=dist.ReduceOp.MAX, group=group)
+        alloc = _alloc or (lambda shape, dt: _symmetric_tensor(shape, dt, dev, plan.rank, plan.world, group))
+        self._bufs, self._tables, self._keep = [], [], []
+        for _ in range(buffers):
+            t, ptrs, keep = alloc((int(rows), n_feat), dtype)
+            self._bufs.append(t)
+            self._tables.append(torch.tensor(ptrs, dtype=torch.int64, device=dev))
+            self._keep.append(keep)
+        flags, fptrs, keep = alloc((max(plan.world, 1),), torch.int64)
+        flags.zero_()
+        self._flags, self._flag_table = flags, torch.tensor(fptrs, dtype=torch.int64, device=dev)
+        self._keep.append(keep)
+        self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._epoch, self._cur = 0, 0
+        self.use_barrier = plan.world > 1 and _alloc is None
+        if self.use_barrier:   # flags are zero everywhere before the first flag store can arrive
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group, device_ids=[dev.index])
+
+    @property
+    def x_ext(self) -> torch.Tensor:
+        return self._bufs[self._cur][: self.plan.n_local + self.plan.n_halo]
+
+    @property
+    def x_local(self) -> torch.Tensor:
+        """This rank's own feature rows: produce the layer input in place here (head of the [local ; halo] buffer)."""
+        return self._bufs[self._cur][: self.plan.n_local]
+
+    def flip(self) -> None:
+        self._cur = (self._cur + 1) % len(self._bufs)
+
+    def barrier(self) -> None:
+        self._epoch += 1
+        dev = self._flags.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().pna_peer_barrier(self._flag_table.data_ptr(), self.plan.rank, self.plan.world, self._epoch, 0,
+                                                   self._status.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+
+    def exchange(self) -> None:
+        p = self.plan
+        if self.use_barrier:
+            self.barrier()
+        if p.n_halo == 0:
+            return
+        buf = self._bufs[self._cur]
+        dt = {torch.float32: _lib.PNA_F32, torch.bfloat16: _lib.PNA_BF16}[self.dtype]
+        dev = buf.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().pna_halo_pull(self._tables[self._cur].data_ptr(), buf.stride(0), p.enc.data_ptr(), p.shift, p.n_halo,
+                                                buf[p.n_local:].data_ptr(), buf.stride(0), self.n_feat, dt,
+                                                torch.cuda.current_stream(dev).cuda_stream))
+
+    def aggregate(self, aggregators, scalers, avg_deg, out: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+        self.exchange()
+        return aggregate_forward(self.x_ext, self.csr, aggregators, scalers, avg_deg, out=out, **kw)
+
+    def check(self) -> None:
+        """Host-side check (synchronises): did every barrier see all peers arrive?"""
+        if int(self._status.item()) != 0:
+            raise RuntimeError("pna_peer_barrier timed out: a peer rank did not reach the barrier")
+
+
+def _symmetric_tensor(shape, dtype, dev, rank: int, world: int, group):
+    """A tensor of `shape` on every rank, each mapped into every process; (local tensor, per-rank pointers, keepalive)."""
+    numel = 1
+    for d in shape:
+        numel *= int(d)
+    rows = _symmetric_rows(1, max(numel, 1), dtype, dev, rank, world, group)
+    return rows[0].view(-1)[:numel].view(*shape), rows[1], rows[2]
+
+
 class PeerAggregator:
     """Gather fused with the exchange: remote rows are read over NVLink inside the aggregation kernel."""
 

@@ -130,3 +130,65 @@ def algorithmic_bytes(n_nodes: int, n_edges: int, n_feat: int, elem_size: int, n
     """compulsory traffic B_min and the no-reuse gather model B_gather, in bytes."""
     fixed = 4 * n_edges + 4 * (n_nodes + 1) + n_out_cols * n_nodes * elem_size
     return {"b_min": n_nodes * n_feat * elem_size + fixed, "b_gather": n_edges * n_feat * elem_size + fixed}
+
+
+# ---- device-side generators for the multi-GPU configs (each rank generates only what it owns) -------------------------
+def hash_features(ids: torch.Tensor, n_feat: int, dtype=torch.float32, chunk: int = 1 << 17) -> torch.Tensor:
+    """x[r, j] = f(ids[r], j): a 32-bit integer mix mapped to [-1, 1) on a 2^-23 grid.  Integer arithmetic only, so the
+    CPU (oracle) and every GPU rank produce bit-identical rows for any subset of node ids without communicating."""
+    ids = ids.to(torch.int64)
+    out = torch.empty((ids.numel(), n_feat), dtype=dtype, device=ids.device)
+    j = torch.arange(n_feat, dtype=torch.int64, device=ids.device) * 0x85EBCA77
+    for r0 in range(0, ids.numel(), chunk):
+        h = (ids[r0:r0 + chunk, None] * 0x9E3779B1 + j[None, :] + 0x165667B1) & 0xFFFFFFFF
+        h ^= h >> 15
+        h = (h * 0x2C1B3C6D) & 0xFFFFFFFF
+        h ^= h >> 12
+        h = (h * 0x297A2D39) & 0xFFFFFFFF
+        h ^= h >> 15
+        out[r0:r0 + chunk] = ((h >> 8).to(torch.float32) * (2.0 ** -23) - 1.0).to(dtype)
+    return out
+
+
+def superpixel_shard(g0: int, n_graphs: int, device, nodes_per_graph: int = 70, k: int = 8, seed: int = 0, chunk: int = 2500):
+    """config 4, graphs g0 .. g0+n_graphs-1 of the 60 000 (graph-batch shard of one rank), generated on `device`: kNN graphs
+    over random 2-D coordinates, every node sends an edge to each of its k nearest neighbours
+    (reference realworld_benchmark/data/superpixels.py:56-75,142-148).  One RNG stream per chunk of `chunk` graphs, so a
+    graph does not depend on how many ranks share the batch.  Returns a LOCAL edge_index (node ids relative to g0)."""
+    n = nodes_per_graph
+    while n_graphs % chunk or g0 % chunk:
+        chunk //= 2
+        if chunk < 1:
+            chunk = 1
+            break
+    srcs, dsts = [], []
+    for c0 in range(g0, g0 + n_graphs, chunk):
+        c = min(chunk, g0 + n_graphs - c0)
+        g = torch.Generator(device=device).manual_seed(seed * 1_000_003 + c0)
+        pos = torch.rand(c, n, 2, generator=g, device=device)
+        d = torch.cdist(pos, pos)
+        d.diagonal(dim1=1, dim2=2).fill_(float("inf"))
+        nbr = d.topk(k, dim=2, largest=False).indices
+        base = ((torch.arange(c0, c0 + c, device=device) - g0) * n).view(c, 1, 1)
+        srcs.append((torch.arange(n, device=device).view(1, n, 1).expand(c, n, k) + base).reshape(-1))
+        dsts.append((nbr + base).reshape(-1))
+    return torch.stack([torch.cat(srcs), torch.cat(dsts)])
+
+
+def powerlaw_stream(n_nodes: int, n_edges: int, device, seed: int = 0, alpha: float = 1.5, chunk: int = 12_500_000):
+    """config 5 as a stream of edge chunks generated on `device` (every rank runs the same stream and keeps what it owns):
+    Zipf(alpha) source and destination ids over random permutations, as :func:`powerlaw`.  Yields (src, dst) int64."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    perm_s = torch.randperm(n_nodes, generator=g, device=device)
+    perm_d = torch.randperm(n_nodes, generator=g, device=device)
+    a = alpha - 1.0
+    hi = float(n_nodes + 1)
+
+    def zipf_ids(n):
+        u = torch.rand(n, generator=g, dtype=torch.float64, device=device)
+        r = (1.0 - u * (1.0 - hi ** (-a))).pow(-1.0 / a)
+        return (r.long() - 1).clamp_(0, n_nodes - 1)
+
+    for e0 in range(0, n_edges, chunk):
+        c = min(chunk, n_edges - e0)
+        yield perm_s[zipf_ids(c)], perm_d[zipf_ids(c)]
