@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <cuda_runtime_api.h>
 #include "pna_b200.h"
 
@@ -16,7 +17,7 @@
 
 static void* dmalloc(size_t bytes) { void* p = NULL; return cudaMalloc(&p, bytes ? bytes : 4) == cudaSuccess ? p : NULL; }
 
-int main(void) {
+int main(int argc, char** argv) {
   enum { N = 5, E = 6, F = 4 };
   /* edges j -> i (PyG: row 0 = source j, row 1 = target i); node 4 has no in-edge */
   const int64_t src[E] = {1, 2, 3, 0, 2, 4}, dst[E] = {0, 0, 0, 1, 1, 3};
@@ -59,6 +60,13 @@ int main(void) {
   PNA(pna_aggregate_fwd(&d, NULL));
   float out[N * 12 * F];
   CU(cudaMemcpy(out, d_out, sizeof out, cudaMemcpyDeviceToHost));
+  if (argc > 1 && strcmp(argv[1], "--dump") == 0) {   /* every value, one row per line (tests/test_gpu_parity.py diffs it) */
+    for (int r = 0; r < N; ++r) {
+      for (int c = 0; c < 12 * F; ++c) printf("%s%.9g", c ? " " : "", out[r * 12 * F + c]);
+      printf("\n");
+    }
+    return 0;
+  }
   for (int r = 0; r < N; r += 4) {            /* row 0: three in-edges; row 4: none -> [0, 0, 0, sqrt(1e-5)] blocks */
     printf("row %d (in-degree %d):", r, indeg[r]);
     for (int c = 0; c < 4 * F; ++c) printf(" %.4f", out[r * 12 * F + c]);

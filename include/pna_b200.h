@@ -202,7 +202,9 @@ typedef struct pna_agg {
    * col indexes `gathered` directly.  All ranks use the same ld_gathered. */
   const void* const* peer_gathered;
   int32_t peer_shift;
-  int32_t reserved;
+  int32_t max_degree;        /* pna_csr_t.max_degree, or 0 = unknown.  A row with more than 64 * 8 chunks (power-law graphs:
+                              * millions of in-edges) has its chunk partials merged by a radix tree of small launches over the
+                              * chunk array instead of by one CTA walking them -- same fixed order on every call */
   /* optional int32 [9 * n_hubs] completion counters, ZERO before the first call (the library leaves them zero): when
    * given together with a view that contains the chunk pseudo-rows, the warp that stores the last partial of a split row
    * also merges and finalizes it (same merge order as the separate finalize kernel), so a layer call is ONE launch with

@@ -120,7 +120,7 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
         avg_log=float(avg_deg["log"]), avg_lin=float(avg_deg.get("lin", 1.0)),
         flags=flags, split_threshold=csr.split_threshold, chunk_edges=csr.chunk_edges,
         hub_info=_ptr(csr.hub_info) if csr.n_hubs else None, chunk_items=_ptr(csr.chunk_items) if csr.n_hubs else None,
-        n_hubs=csr.n_hubs, n_chunks=csr.n_chunks, hub_partials=_ptr(partials),
+        n_hubs=csr.n_hubs, n_chunks=csr.n_chunks, hub_partials=_ptr(partials), max_degree=int(csr.max_degree),
         row_ids=_ptr(row_ids), n_row_ids=0 if row_ids is None else int(row_ids.numel()))
     if scaler_degree is not None:
         d.scaler_degree = _check_scaler_degree(scaler_degree, N, dev).data_ptr()

@@ -66,10 +66,12 @@ extern "C" int pna_aggregate_fwd(const pna_agg_t* d, pna_stream_t stream) {
               "pna_aggregate_fwd: n_view_rows must be n_rows + n_chunks");
   p.n_fpass = 0;
   p.sdeg = d->scaler_degree;
+  // more than 512 chunks in one row: merge the partials with the radix tree (k_hub_tree) before the finalize
+  p.hub_merged = (d->max_degree > 0 && (long long)d->max_degree > 512ll * d->chunk_edges) ? 1 : 0;
   p.peer_x = reinterpret_cast<const void* const*>(d->peer_gathered); p.peer_shift = d->peer_shift;
   if (p.peer_x) PNA_REQUIRE(d->peer_shift >= 1 && d->peer_shift <= 30, PNA_ERR_BAD_ARG, "pna_aggregate_fwd: peer_shift out of range");
-  PNA_REQUIRE(p.ldx < 0x7fffffffll && p.ldb < 0x7fffffffll && p.lds < 0x7fffffffll, PNA_ERR_UNSUPPORTED,
-              "pna_aggregate_fwd: row pitch too large");
+  PNA_REQUIRE(p.ldx < 0x3fffffffll && p.ldb < 0x7fffffffll && p.lds < 0x7fffffffll, PNA_ERR_UNSUPPORTED,
+              "pna_aggregate_fwd: row pitch too large");     // ld_gathered in BYTES is a 32-bit kernel operand
   PNA_REQUIRE(p.ldo >= (long long)p.T * p.Wt, PNA_ERR_BAD_ARG, "pna_aggregate_fwd: ld_out %lld < row width %lld",
               (long long)p.ldo, (long long)p.T * p.Wt);
 

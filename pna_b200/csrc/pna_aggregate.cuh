@@ -36,6 +36,7 @@ struct KParams {
   const int* row_ids; long long n_row_ids;
   const int* lrowptr; const int* ldeg; const int* lcol; const int* part; int n_part;   // light view (nullable)
   long long n_view_rows;   // > n_rows: view rows n_rows + c are chunk pseudo-rows reduced into partials[c]
+  int hub_merged;          // 1: every split row's total already sits in its first partial slot (k_hub_tree ran)
   const int* sdeg;         // nullable [n_rows]: degree seen by the scalers (default: the in-degree of the row)
   int n_fpass;             // > 1: the streamed kernel makes this many passes over its rows, one feature block each
   const void* const* peer_x; int peer_shift;   // multi-GPU: x of every rank (NVLink peer pointers), col = owner << shift | row
@@ -247,15 +248,88 @@ __device__ __forceinline__ void accumulate_slots(const KParams& p, const FeatMap
   if (e < end) accumulate_batch<T, VEC, G, K, U, false>(p, col, fm, e, end, bias, has_bias, acc);
 }
 
+// Correctly rounded x / d for MANY numerators and ONE divisor (the in-degree): r = RN(1/d) once, then per numerator
+// q = RN(x r), e = x - q d (exact, one FMA), x/d = RN(q + e r) -- Markstein's theorem: with a correctly rounded reciprocal and
+// q within one ulp of the quotient the corrected q is the correctly rounded quotient (the sequence IEEE division itself ends
+// with).  3 instructions per quotient instead of the ~9 of div.rn.f32; the same bits (tests/test_gpu_parity.py compares it
+// with the CPU's division on random and adversarial operands).  Quotients below the normal range may differ by one
+// subnormal ulp (1.4e-45).
+struct SharedDivisor {
+  float d, r;
+#ifdef __CUDA_ARCH__   // (the host pass of nvcc parses this non-template struct but has no device intrinsics)
+  __device__ __forceinline__ explicit SharedDivisor(float d_) : d(d_), r(__frcp_rn(d_)) {}
+  __device__ __forceinline__ float operator()(float x) const {
+    const float q = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-q, d, x);
+    return __fmaf_rn(e, r, q);
+  }
+#else
+  explicit SharedDivisor(float d_) : d(d_), r(1.0f / d_) {}
+  float operator()(float x) const { return x / d; }
+#endif
+};
+
+// A row without in-edges (PyG semantics, aggregators.py:13-32 / scalers.py:8-29 at d = 0): mean = min = max = sum = var = 0,
+// std = sqrt(1e-5); amplification = log(1)/delta = 0, attenuation = linear-inverse = 1, linear = 0 -- every output segment is
+// one constant splat.  Power-law graphs consist mostly of such rows (94 % in config 5), so they get their own short path.
+template <typename T, int VEC, int G, int K, typename Cfg>
+__device__ __forceinline__ void finalize_isolated_row(const KParams& p, const FeatMap<VEC, G, K>& fm, long long row) {
+  const int nA = Cfg::kStatic ? Cfg::NA : p.nA, nS = Cfg::kStatic ? Cfg::NS : p.nS;
+  const unsigned acodes = Cfg::kStatic ? Cfg::ACODES : p.acodes, scodes = Cfg::kStatic ? Cfg::SCODES : p.scodes;
+  const bool zero_all = (p.flags & PNA_FLAG_ZERO_ISOLATED) != 0;
+  const float sd0 = __fsqrt_rn(__fadd_rn(0.0f, 1e-5f));
+  const DegScales ds = deg_scales(0, p.avg_log, p.avg_lin);
+  T* __restrict__ orow = static_cast<T*>(p.out) + row * p.ldo;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    if (!fm.ok[k]) continue;
+    if (p.self) {
+      float sv[VEC];
+      Io<T, VEC>::load(static_cast<const T*>(p.self) + row * p.lds + fm.sin[k], sv);
+      Io<T, VEC>::store(orow + fm.soff[k], sv);
+    }
+    T* __restrict__ obase = orow + fm.ooff[k];
+#pragma unroll
+    for (int a = 0; a < Cfg::NA; ++a) {
+      if (!Cfg::kStatic && a >= nA) break;
+      const unsigned ac = (acodes >> (4 * a)) & 15u;
+      if (ac == PNA_AGGR_SKIP) continue;
+      const float base = (ac == PNA_AGGR_STD && !zero_all) ? sd0 : 0.0f;
+#pragma unroll
+      for (int s = 0; s < Cfg::NS; ++s) {
+        if (!Cfg::kStatic && s >= nS) break;
+        const unsigned sc = (scodes >> (4 * s)) & 15u;
+        const float v = (sc == PNA_SCALE_IDENTITY) ? base : __fmul_rn(base, ds.of(sc));
+        float o[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = v;
+        Io<T, VEC>::store(obase + (s * nA + a) * p.Ft, o);
+      }
+    }
+  }
+}
+
+// mean/var/std + scalers + the S*A streaming stores of one row; `ds` = the row's degree-scaler factors.
+template <typename T, int VEC, int G, int K, typename Cfg>
+__device__ __forceinline__ void finalize_row_ds(const KParams& p, const FeatMap<VEC, G, K>& fm, long long row, int deg,
+                                                const DegScales& ds, const Acc<VEC> (&acc)[K]);
+
 // mean/var/std + scalers + the S*A streaming stores of one row.
 template <typename T, int VEC, int G, int K, typename Cfg>
 __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC, G, K>& fm, long long row, int deg,
                                              const Acc<VEC> (&acc)[K]) {
+  // unused factors are dead code under a static Cfg; the scalers' degree may be supplied separately (dense layer)
+  const DegScales ds = deg_scales(p.sdeg ? __ldg(p.sdeg + row) : deg, p.avg_log, p.avg_lin);
+  finalize_row_ds<T, VEC, G, K, Cfg>(p, fm, row, deg, ds, acc);
+}
+
+template <typename T, int VEC, int G, int K, typename Cfg>
+__device__ __forceinline__ void finalize_row_ds(const KParams& p, const FeatMap<VEC, G, K>& fm, long long row, int deg,
+                                                const DegScales& ds, const Acc<VEC> (&acc)[K]) {
   const bool iso = deg == 0;
   const float degf = (float)deg;
   const float cnt = iso ? 1.0f : degf;                     // count.clamp_(1)
-  // unused factors are dead code under a static Cfg; the scalers' degree may be supplied separately (dense layer)
-  const DegScales ds = deg_scales(p.sdeg ? __ldg(p.sdeg + row) : deg, p.avg_log, p.avg_lin);
+  const SharedDivisor by_cnt(cnt);
   const bool zero_all = iso && (p.flags & PNA_FLAG_ZERO_ISOLATED);
   const int nA = Cfg::kStatic ? Cfg::NA : p.nA, nS = Cfg::kStatic ? Cfg::NS : p.nS;
   const unsigned acodes = Cfg::kStatic ? Cfg::ACODES : p.acodes, scodes = Cfg::kStatic ? Cfg::SCODES : p.scodes;
@@ -272,8 +346,8 @@ __device__ __forceinline__ void finalize_row(const KParams& p, const FeatMap<VEC
     float mean[VEC], var[VEC], sd[VEC], mn[VEC], mx[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      mean[i] = __fdiv_rn(acc[k].sum[i], cnt);                                   // aggregators.py:13-14
-      const float msq = __fdiv_rn(acc[k].sq[i], cnt);
+      mean[i] = by_cnt(acc[k].sum[i]);                                           // aggregators.py:13-14 (true divide)
+      const float msq = by_cnt(acc[k].sq[i]);
       var[i] = __fsub_rn(msq, __fmul_rn(mean[i], mean[i]));                      // aggregators.py:25-28
       sd[i] = __fsqrt_rn(__fadd_rn(fmaxf(var[i], 0.0f), 1e-5f));                 // aggregators.py:31-32
       mn[i] = iso ? 0.0f : acc[k].mn[i];                                         // aggregators.py:17-22 (empty -> 0)

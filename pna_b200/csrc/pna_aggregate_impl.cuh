@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
 // Gather latency is hidden by bytes in flight in shared memory instead of by registers or by more warps:
 // 24 warps x 8 KB per SM versus 24 warps x 4 x 512 B with register staging.
 constexpr int kStreamThreads = 128;
+constexpr int kScaleLut = 256;       // in-degrees with precomputed scaler factors (rows at/above it: computed per row)
 
 __device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -431,9 +432,18 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   constexpr int H = StreamGeom<T, VEC, K, DEPTH>::kH;
   constexpr int SLOT = StreamGeom<T, VEC, K, DEPTH>::kBlockBytes;
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr bool PEER = DEPTH > 1;     // the deep-ring instantiations are the ones launched with peer pointers
   extern __shared__ __align__(128) unsigned char smem[];
+  // degree-scaler factors of every in-degree below kScaleLut: one shared-memory read per row instead of logf + two IEEE
+  // divisions per lane per row (the same device function fills the table, so the factors keep their bits)
+  __shared__ float4 s_scale_lut[kScaleLut];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kScaleLut; i += kStreamThreads) {
+    const DegScales dsi = deg_scales(i, p.avg_log, p.avg_lin);
+    s_scale_lut[i] = make_float4(dsi.amp, dsi.att, dsi.lin, dsi.ilin);
+  }
+  __syncthreads();
 
   // this warp's rows: a contiguous range of the light view, cut at equal-cost partition boundaries
   const long long W = (long long)gridDim.x * (kStreamThreads / 32);
@@ -473,8 +483,13 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   FeatMap<VEC, G, K> fm;
   fm.init(p, lane, fblock);
 
-  // source row of stream position q for this lane (lanes >= H or q >= Te: -1)
+  // source row of stream position q for this lane.  Past the end of the stream (and for lanes >= H) it is row 0: the
+  // ring slot is filled with a row nobody reads, which keeps every copy unconditional -- no per-slot branch
+#if PNA_STREAM_TMA
   auto source_of = [&](int q) -> int { return (lane < H && q < Te) ? __ldg(lcol + q) : -1; };
+#else
+  auto source_of = [&](int q) -> int { return (lane < H && q < Te) ? __ldg(lcol + q) : 0; };
+#endif
   // issue the copies of half n (positions n*H .. n*H+H-1) whose sources were fetched one step earlier
 #if PNA_STREAM_TMA
   auto issue_half = [&](int n, int src) {
@@ -487,18 +502,20 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   // every lane copies ITS OWN 16-byte chunk(s) of each neighbour row, and later reads exactly those bytes back:
   // completion is tracked per thread by cp.async groups, no cross-lane synchronisation is needed at all
   const int lane_elems = fblock + lane * VEC;   // this lane's first 16-byte chunk inside a gathered row
+  // byte address of this lane's chunk in row 0; a row is one unsigned 32 x 32 -> 64-bit multiply-add away (IMAD.WIDE.U32)
+  const char* const xlane = reinterpret_cast<const char*>(static_cast<const T*>(p.x) + lane_elems);
+  const unsigned ldxb = (unsigned)p.ldx * (unsigned)sizeof(T);
   auto issue_half = [&](int n, int src) {
-    const int nvalid = min(H, Te - n * H);
     unsigned dst = ring + (unsigned)((n & 1) * H) * SLOT + lane * CB;
 #pragma unroll
     for (int u = 0; u < H; ++u, dst += SLOT) {
       const int s_u = __shfl_sync(FULL, src, u);
-      if (u < nvalid) {
-        const T* sp = gathered_row<T>(p, s_u) + lane_elems;
+      const char* sp;
+      if constexpr (PEER) sp = reinterpret_cast<const char*>(gathered_row<T>(p, s_u) + lane_elems);
+      else sp = xlane + (unsigned long long)(unsigned)s_u * ldxb;
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-          if (fm.ok[k]) cp_async_chunk<CB>(dst + k * (32 * CB), sp + k * (32 * VEC), keep);
-      }
+      for (int k = 0; k < K; ++k)
+        if (fm.ok[k]) cp_async_chunk<CB>(dst + k * (32 * CB), sp + k * (32 * CB), keep);
     }
     cp_async_commit();
   };
@@ -607,7 +624,19 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
         }
       }
       if (!chunk_row) {
-        finalize_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, acc);
+        if (deg == 0 && !p.sdeg) {
+          finalize_isolated_row<T, VEC, G, K, Cfg>(p, fm, (long long)row);
+        } else {
+          DegScales ds;
+          const int sd = p.sdeg ? __ldg(p.sdeg + row) : deg;      // the scalers' degree may be supplied separately (dense layer)
+          if (sd < kScaleLut) {
+            const float4 t = s_scale_lut[sd];
+            ds.amp = t.x; ds.att = t.y; ds.lin = t.z; ds.ilin = t.w;
+          } else {
+            ds = deg_scales(sd, p.avg_log, p.avg_lin);
+          }
+          finalize_row_ds<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, ds, acc);
+        }
       } else {
         float* __restrict__ part = p.partials + (long long)(row - (int)p.n_rows) * 4ll * p.F;
 #pragma unroll
@@ -666,6 +695,94 @@ __global__ void __launch_bounds__(kThreads, min_blocks(VEC, K)) k_hub_chunks(con
   }
 }
 
+// ---- split rows with very many chunks (power-law graphs: millions of in-edges in one row) ---------------------------------
+// One CTA walking a row's chunk partials (k_hub_finalize) is a serial tail of tens of thousands of dependent 4 KB reads.
+// Instead the partials are merged by a radix tree over the GLOBAL chunk array: at the level with stride S a warp owns the
+// block of R*S chunk positions [B*R*S, (B+1)*R*S) and visits its positions B*R*S + j*S, j = 1..R-1; a position that is a
+// CONTINUATION of a split row (the row's first chunk lies before it) holds that row's parked partial for
+// [pos, pos + S) from the level below and is added, in position order, into the row's head inside this block,
+// max(first chunk of the row, B*R*S).  After ceil(log_R(n_chunks)) levels every row's total sits in its first chunk's slot.
+// Fixed order for a given graph -> deterministic, no atomics; every level is one small launch.
+constexpr int kTreeR = 32;
+
+template <int VEC, int K>
+__global__ void __launch_bounds__(128) k_hub_tree(const KParams p, long long S) {
+  constexpr int G = 32;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long long B = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const long long base = B * kTreeR * S;
+  if (base >= p.n_chunks) return;
+  FeatMap<VEC, G, K> fm;
+  fm.init(p, lane, blockIdx.y * (G * VEC * K));
+  // lane j: is position base + j*S a continuation, and of which head?
+  long long my_head = -1;
+  {
+    const long long pos = base + (long long)lane * S;
+    if (lane > 0 && pos < p.n_chunks) {
+      const int h = __ldg(p.chunk_items + 2 * pos);
+      const long long first = __ldg(p.hub_info + 4 * h + 1);
+      if (first < pos) my_head = first > base ? first : base;
+    }
+  }
+  const long long F4 = 4ll * p.F;
+  auto load = [&](long long c, Acc<VEC> (&a)[K]) {
+    const float* part = p.partials + c * F4;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (!fm.ok[k]) continue;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        a[k].sum[i] = __ldcg(part + 0ll * p.F + fm.f[k] + i);
+        a[k].sq[i] = __ldcg(part + 1ll * p.F + fm.f[k] + i);
+        a[k].mn[i] = __ldcg(part + 2ll * p.F + fm.f[k] + i);
+        a[k].mx[i] = __ldcg(part + 3ll * p.F + fm.f[k] + i);
+      }
+    }
+  };
+  auto store = [&](long long c, const Acc<VEC> (&a)[K]) {
+    float* part = p.partials + c * F4;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (!fm.ok[k]) continue;
+      store_f32<VEC>(part + 0ll * p.F + fm.f[k], a[k].sum);
+      store_f32<VEC>(part + 1ll * p.F + fm.f[k], a[k].sq);
+      store_f32<VEC>(part + 2ll * p.F + fm.f[k], a[k].mn);
+      store_f32<VEC>(part + 3ll * p.F + fm.f[k], a[k].mx);
+    }
+  };
+  Acc<VEC> acc[K];
+  long long cur = -1;
+#pragma unroll 1
+  for (int j = 1; j < kTreeR; j += 2) {
+    const long long h0 = __shfl_sync(FULL, my_head, j);
+    const long long h1 = (j + 1 < kTreeR) ? __shfl_sync(FULL, my_head, j + 1) : -1;
+    if (h0 < 0 && h1 < 0) continue;
+    Acc<VEC> t0[K], t1[K];
+    if (h0 >= 0) load(base + (long long)j * S, t0);          // both loads in flight before the dependent adds
+    if (h1 >= 0) load(base + (long long)(j + 1) * S, t1);
+    auto fold = [&](long long head, const Acc<VEC> (&t)[K]) {
+      if (head != cur) {
+        if (cur >= 0) store(cur, acc);
+        load(head, acc);
+        cur = head;
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          acc[k].sum[i] = __fadd_rn(acc[k].sum[i], t[k].sum[i]);
+          acc[k].sq[i] = __fadd_rn(acc[k].sq[i], t[k].sq[i]);
+          acc[k].mn[i] = fminf(acc[k].mn[i], t[k].mn[i]);
+          acc[k].mx[i] = fmaxf(acc[k].mx[i], t[k].mx[i]);
+        }
+    };
+    if (h0 >= 0) fold(h0, t0);
+    if (h1 >= 0) fold(h1, t1);
+  }
+  if (cur >= 0) store(cur, acc);
+}
+
 // ---- hubs, pass 2 (k_hub_finalize): merge_partials / kFinGroups are defined above k_rows_stream ------------------------
 template <typename T, int VEC, int G, int K>
 __global__ void __launch_bounds__(kFinGroups * 32) k_hub_finalize(const KParams p) {
@@ -683,8 +800,11 @@ __global__ void __launch_bounds__(kFinGroups * 32) k_hub_finalize(const KParams 
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k].init();
 
-  const bool two_level = nch > kFinGroups;
-  if (two_level) {
+  const bool two_level = nch > kFinGroups && !p.hub_merged;
+  if (p.hub_merged) {     // k_hub_tree left the row's total in its first chunk's slot
+    if (q != 0) return;
+    merge_partials<VEC, K, UF>(p.partials, p.F, fm.f, fm.ok, first, 1, 1, acc);
+  } else if (two_level) {
     const int mine = (nch - q + kFinGroups - 1) / kFinGroups;     // chunks q, q+kFinGroups, ..
     merge_partials<VEC, K, UF>(p.partials, p.F, fm.f, fm.ok, first + q, mine, kFinGroups, acc);
     float* part = p.partials + (long long)(first + q) * 4ll * p.F;
@@ -729,7 +849,7 @@ static int launch_config(const KParams& p_in, cudaStream_t st) {
   KParams p = p_in;
   const unsigned gy = (unsigned)((p.F + G * VEC * K - 1) / (G * VEC * K));
   // folded finalize: one counter set per split row, i.e. one feature block, and only the streamed kernel implements it
-  if (gy != 1 || !(p.n_view_rows > p.n_rows)) p.hub_done = nullptr;
+  if (gy != 1 || !(p.n_view_rows > p.n_rows) || p.hub_merged) p.hub_done = nullptr;
   bool folded = false;
   bool chunks_in_stream = false;   // the streamed kernel also reduced the chunks of the split rows
   if (!(p.flags & PNA_FLAG_SKIP_LIGHT)) {
@@ -823,6 +943,17 @@ static int launch_config(const KParams& p_in, cudaStream_t st) {
       PNA_CUDA_TRY(cudaGetLastError());
     }
     if (!folded) {
+      if constexpr (G == 32) {
+        if (p.hub_merged) {
+          for (long long S = 1; S < p.n_chunks; S *= kTreeR) {
+            const long long blocks = (p.n_chunks + kTreeR * S - 1) / (kTreeR * S);
+            k_hub_tree<VEC, K><<<dim3((unsigned)((blocks + 3) / 4), gy), 128, 0, st>>>(p, S);
+            PNA_CUDA_TRY(cudaGetLastError());
+          }
+        }
+      } else {
+        p.hub_merged = 0;     // narrow rows keep the CTA-per-row merge
+      }
       k_hub_finalize<T, VEC, G, K><<<dim3((unsigned)p.n_hubs, gy), kFinGroups * G, 0, st>>>(p);
       PNA_CUDA_TRY(cudaGetLastError());
     }

@@ -836,3 +836,55 @@ def test_readouts_match_torch_segment_ops(P):
     torch.testing.assert_close(R.sum_nodes(gr, "h").cpu(), want_sum, rtol=1e-5, atol=5e-5)
     torch.testing.assert_close(R.mean_nodes(gr, "h").cpu(), want_sum / cnt, rtol=1e-5, atol=1e-5)
     assert torch.equal(R.max_nodes(gr, "h").cpu(), want_max)
+
+
+# ---- the ABI driven from plain C (examples/c_caller.c), executed and diffed against the C oracle -------------------------
+def test_plain_c_caller_runs_and_matches_the_c_oracle(P):
+    import os, subprocess, tempfile
+    from oracle import c_oracle
+    from pna_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "c_caller")
+        r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                            os.path.join(root, "examples", "c_caller.c"), "-o", exe, "-L", os.path.dirname(_lib.LIB_PATH),
+                            "-l:" + os.path.basename(_lib.LIB_PATH), "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+                            "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        r = subprocess.run([exe, "--dump"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+    got = torch.tensor([[float(v) for v in line.split()] for line in r.stdout.strip().splitlines()])
+    # the graph and features hard-coded in examples/c_caller.c
+    ei = torch.tensor([[1, 2, 3, 0, 2, 4], [0, 0, 0, 1, 1, 3]])
+    x = ((torch.arange(20) % 7).float() - 3.0).view(5, 4)
+    indeg = torch.tensor([3.0, 2.0, 0.0, 1.0, 0.0])
+    avg = {"log": float(sum(math.log(d + 1.0) / 5 for d in indeg.tolist())), "lin": 1.0}
+    want = c_oracle.aggregate(x, ei, A4, S3, avg)
+    assert got.shape == want.shape == (5, 48)
+    torch.testing.assert_close(got, want, rtol=2e-6, atol=1e-7)     # mean/min/max exact; avg_log summed in float vs double
+
+
+# ---- the shared-divisor division of the epilogue (SharedDivisor, csrc/pna_aggregate.cuh) is IEEE division ------------------
+def test_mean_and_var_division_is_bit_identical_for_large_in_degrees(P, O):
+    """mean = sum / d and E[m^2] = sumsq / d go through q = RN(x r), e = x - q d, RN(q + e r) with r = RN(1/d).  With the
+    split threshold raised, rows of up to several thousand in-edges are reduced sequentially like the reference does, so
+    sum (bit-identical, sequential fp32) / d must reproduce the CPU's IEEE division bit for bit for every divisor seen --
+    checked on the mean columns and, through the plain-C oracle, on the unscaled std columns."""
+    from oracle import c_oracle
+    g = torch.Generator().manual_seed(77)
+    n, f = 700, 128
+    degs = torch.cat([torch.arange(1, 300), torch.randint(300, 6000, (300,), generator=g), torch.tensor([4095, 4096, 4097, 8191])])
+    dst = torch.repeat_interleave(torch.arange(degs.numel()), degs)
+    src = torch.randint(0, n, (dst.numel(),), generator=g)
+    p = torch.randperm(dst.numel(), generator=g)
+    ei = torch.stack([src[p], dst[p]])
+    # wide dynamic range in the features: quotients with every kind of mantissa
+    x = torch.randn(n, f, generator=g) * torch.exp(4 * torch.randn(n, 1, generator=g))
+    avg = avg_deg_of(ei, n, O)
+    csr = P.build_csr(ei[0].to(dev()), ei[1].to(dev()), n, split_threshold=16384, chunk_edges=128)
+    assert csr.n_hubs == 0
+    got = P.aggregate_forward(x.to(dev()), csr, A4, ["identity"], avg).cpu()
+    want = c_oracle.aggregate(x, ei, A4, ["identity"], avg)
+    assert torch.equal(got[:, :3 * f], want[:, :3 * f])                       # mean, max, min: bit for bit
+    assert torch.equal(got[:, 3 * f:], want[:, 3 * f:])                       # std = sqrt(relu(sumsq/d - mean^2) + eps), IEEE sqrt
