@@ -156,7 +156,8 @@ def side_configs(dev, flush, steps, peak):
         rec = {"workload": note, "n_nodes": n, "n_edges": e, "n_feat": f, "dtype": str(x.dtype).replace("torch.", ""), "ms_per_step": ms,
                "edges_per_s": e / (ms * 1e-3), "b_min_bytes": by["b_min"], "frac_of_measured_hbm_peak": by["b_min"] / (ms * 1e-3) / 1e9 / peak,
                "split_rows": csr.n_hubs, "max_in_degree": csr.max_degree, "parity_ok": par["ok"],
-               "parity_max_err": max(par["max_err_light"], par["max_err_split_vs_f64"]), "parity_rows": par["rows"] + par["big_rows"],
+               "parity_max_err": max(par["max_err_light"], par["max_err_split_vs_f64"]), "parity_max_err_over_tolerance": par["max_err_over_tol"],
+               "parity_rows": par["rows"] + par["big_rows"],
                "parity_rows_are_all_rows": par["rows"] + par["big_rows"] == n}
         if extra:
             rec.update(extra(csr, xd, avg, deg_hist))
@@ -257,13 +258,18 @@ def run_ours(args):
     csr = pna_b200.build_csr(eid[0], eid[1], n)
     torch.cuda.synchronize()
     csr_ms_first = 1e3 * (time.perf_counter() - t0)
+    for _ in range(3):
+        pna_b200.build_csr(eid[0], eid[1], n)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     ev[0].record()
     for _ in range(5):
         pna_b200.build_csr(eid[0], eid[1], n)
     ev[1].record()
     torch.cuda.synchronize()
     csr_ms = ev[0].elapsed_time(ev[1]) / 5
+    csr_wall_ms = 1e3 * (time.perf_counter() - t0) / 5
 
     out = torch.empty((n, 12 * f), dtype=torch.float32, device=dev)
     flush = bc.L2Flush(dev)
@@ -387,6 +393,7 @@ def run_ours(args):
                      "b_min_bytes": bytes_["b_min"], "b_gather_bytes": bytes_["b_gather"],
                      "effective_gbs_b_gather": bytes_["b_gather"] / (t_ms * 1e-3) / 1e9},
         "parity": {"ok": par["ok"], "parity_max_err": max(par["max_err_light"], par["max_err_split_vs_f64"]),
+                   "max_err_over_tolerance": par["max_err_over_tol"], "tolerance": "|d| <= 1e-5 + 1e-5 |want| (north star: 1e-5 fp32)",
                    "max_err_light_rows": par["max_err_light"], "max_err_split_rows_vs_f64": par["max_err_split_vs_f64"],
                    "rows_checked": par["rows"] + par["big_rows"], "split_rows_checked": par["split_rows"] + par["big_rows"],
                    "what": "every row of the timed step's output vs the CPU oracle (fp32 op sequence; rows split across warps vs float64)"},
@@ -398,7 +405,7 @@ def run_ours(args):
                       "what": "PNAConvSimple.forward, CSR cached: aggregation with the identity scaler ([N,4F]) + post-MLP linear on "
                               "the tensor cores regenerating the scaled copies in registers (pna_linear_scaled_fwd, 3xTF32 "
                               "tcgen05); ms_via_12f_tensor = same layer through the materialised [N,12F] tensor"},
-        "csr_build_ms": {"first_call": csr_ms_first, "steady": csr_ms},
+        "csr_build_ms": {"first_call": csr_ms_first, "steady": csr_ms, "steady_wall": csr_wall_ms},
         "e2e": {"value": e / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": x.numel() * 4 + ei.numel() * 8, "d2h_bytes_per_step": n * f * 4,
                 "device_ms_per_step": s2.elapsed_time(e2) / k2, "wall_ms_per_step": e2e_wall_ms,

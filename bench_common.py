@@ -175,7 +175,7 @@ def sampled_parity(out: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, f
     small_rows, small_deg = o2.values, small_deg[o2.indices]
     tol = dict(rtol=1e-5, atol=1e-5) if out.dtype == torch.float32 else dict(rtol=2 ** -8, atol=1e-3)
     res = {"rows": int(small_rows.numel()), "edges": int(small_deg.sum()), "max_err_light": 0.0, "max_err_split_vs_f64": 0.0,
-           "split_rows": 0, "big_rows": 0, "ok": True}
+           "max_err_over_tol": 0.0, "split_rows": 0, "big_rows": 0, "ok": True}
     if small_rows.numel():
         starts = rp[small_rows]
         slot = torch.repeat_interleave(starts - torch.cumsum(small_deg, 0) + small_deg, small_deg) + torch.arange(int(small_deg.sum()))
@@ -189,11 +189,13 @@ def sampled_parity(out: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, f
         if light.any():
             d = (got[light] - want[light]).abs()
             res["max_err_light"] = float(d.max())
+            res["max_err_over_tol"] = max(res["max_err_over_tol"], float((d / (tol["atol"] + tol["rtol"] * want[light].abs())).max()))
             res["ok"] &= bool((d <= tol["atol"] + tol["rtol"] * want[light].abs()).all())
         if (~light).any():
             want64 = O.pyg_aggregate(xu.double()[inv], dst_rel, small_rows.numel(), aggrs, scalers, avg_deg)
             d = (got[~light].double() - want64[~light]).abs()
             res["max_err_split_vs_f64"] = float(d.max())
+            res["max_err_over_tol"] = max(res["max_err_over_tol"], float((d / (tol["atol"] + tol["rtol"] * want64[~light].abs())).max()))
             res["split_rows"] = int((~light).sum())
             res["ok"] &= bool((d <= tol["atol"] + tol["rtol"] * want64[~light].abs()).all())
     # very large rows: streamed float64 reduction of the first columns
@@ -220,6 +222,7 @@ def sampled_parity(out: torch.Tensor, rowptr: torch.Tensor, col: torch.Tensor, f
                 want = vals[ag] * fac[sc]
                 d = (got[si, ai] - want).abs()
                 res["max_err_split_vs_f64"] = max(res["max_err_split_vs_f64"], float(d.max()))
+                res["max_err_over_tol"] = max(res["max_err_over_tol"], float((d / (10 * tol["atol"] + 10 * tol["rtol"] * want.abs())).max()))
                 res["ok"] &= bool((d <= 10 * tol["atol"] + 10 * tol["rtol"] * want.abs()).all())
         res["big_rows"] += 1
     return res

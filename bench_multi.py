@@ -251,6 +251,8 @@ def run(args):
                           "max_in_degree": max(b[6] for b in by_all), "ms_per_step_per_rank": all_ms, "gpu_numa_node": numa,
                           "generation_s": gen_s},
             "parity": {"ok": all(p["ok"] for p in par_all), "parity_max_err": max(max(p["max_err_light"], p["max_err_split_vs_f64"]) for p in par_all),
+                       "max_err_over_tolerance": max(p["max_err_over_tol"] for p in par_all),
+                       "tolerance": "|d| <= 1e-5 + 1e-5 |want| (rows split across warps: vs float64)",
                        "max_err_light_rows": max(p["max_err_light"] for p in par_all),
                        "max_err_split_rows_vs_f64": max(p["max_err_split_vs_f64"] for p in par_all),
                        "rows_checked": sum(p["rows"] + p["big_rows"] for p in par_all), "edges_checked": sum(p["edges"] for p in par_all),

@@ -82,6 +82,24 @@ __device__ __forceinline__ DegScales deg_scales(int deg, float avg_log, float av
 // Gathered rows go through the read-only path (ld.global.nc); the [N, S*A*F] result is written once and never
 // re-read by this library, so it is stored with the streaming (evict-first) policy to keep source rows in L2.
 
+// How the [N, S*A*F] result leaves the SM.  0: st.global.cs (streaming, evict-first) -- the default; 1: plain st.global;
+// 2: st.global.cg; 3: st.global.wt.  A build-time knob for experiments (tools/exp/build_variant.sh).
+#ifndef PNA_STORE_MODE
+#define PNA_STORE_MODE 0
+#endif
+template <typename V>
+__device__ __forceinline__ void store_out(V* p, V v) {
+#if PNA_STORE_MODE == 1
+  *p = v;
+#elif PNA_STORE_MODE == 2
+  __stcg(p, v);
+#elif PNA_STORE_MODE == 3
+  __stwt(p, v);
+#else
+  __stcs(p, v);
+#endif
+}
+
 template <typename T, int VEC>
 struct Io;
 
@@ -92,7 +110,7 @@ struct Io<float, 4> {
   static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[4]) { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
   static __device__ __forceinline__ void load(const float* p, float (&v)[4]) { unpack(load_raw(p), v); }
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
-    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    store_out(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
   }
 };
 
@@ -102,7 +120,7 @@ struct Io<float, 2> {
   static __device__ __forceinline__ Raw load_raw(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
   static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[2]) { v[0] = r.x; v[1] = r.y; }
   static __device__ __forceinline__ void load(const float* p, float (&v)[2]) { unpack(load_raw(p), v); }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[2]) { __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1])); }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[2]) { store_out(reinterpret_cast<float2*>(p), make_float2(v[0], v[1])); }
 };
 
 template <>
@@ -132,7 +150,7 @@ struct Io<__nv_bfloat16, 8> {
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
     uint4 r;
     r.x = pack(v[0], v[1]); r.y = pack(v[2], v[3]); r.z = pack(v[4], v[5]); r.w = pack(v[6], v[7]);
-    __stcs(reinterpret_cast<uint4*>(p), r);
+    store_out(reinterpret_cast<uint4*>(p), r);
   }
 };
 

@@ -67,6 +67,28 @@ __global__ void __launch_bounds__(kThreads, min_blocks(VEC, K)) k_rows(const KPa
 //     gather latency of one row hides behind the arithmetic of the previous one.
 // The slot order inside a row is unchanged (sequential fp32 accumulation in CSR order).
 constexpr int kTiledThreads = 128;   // 4 warps per CTA: small CTAs retire early, keeping more warps resident
+constexpr int kScaleLut = 256;       // in-degrees with precomputed scaler factors (rows at/above it: computed per row)
+
+// degree-scaler factors of every in-degree below kScaleLut in shared memory: one read per row instead of logf + two IEEE
+// divisions per lane per row.  The same device function (deg_scales) fills the table, so the factors keep their bits.
+__device__ __forceinline__ void fill_scale_lut(float4* lut, const KParams& p, int tid, int nthreads) {
+  for (int i = tid; i < kScaleLut; i += nthreads) {
+    const DegScales d = deg_scales(i, p.avg_log, p.avg_lin);
+    lut[i] = make_float4(d.amp, d.att, d.lin, d.ilin);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ DegScales scales_of_row(const float4* lut, const KParams& p, long long row, int deg) {
+  const int sd = p.sdeg ? __ldg(p.sdeg + row) : deg;      // the scalers' degree may be supplied separately (dense layer)
+  DegScales ds;
+  if (sd < kScaleLut) {
+    const float4 t = lut[sd];
+    ds.amp = t.x; ds.att = t.y; ds.lin = t.z; ds.ilin = t.w;
+  } else {
+    ds = deg_scales(sd, p.avg_log, p.avg_lin);
+  }
+  return ds;
+}
 // resident 128-thread CTAs the register allocator leaves room for: 6 -> <= 80 registers (no spills at one 128-bit
 // chunk per lane), i.e. 24 warps/SM, each with U gathers in flight underneath its epilogue
 #ifndef PNA_TILED_MINB
@@ -74,7 +96,9 @@ constexpr int kTiledThreads = 128;   // 4 warps per CTA: small CTAs retire early
 #endif
 constexpr int tiled_min_blocks(int vec, int k) { return vec * k <= 4 ? PNA_TILED_MINB : (vec * k <= 8 ? 4 : (vec * k <= 16 ? 3 : 2)); }
 
-template <typename T, int VEC, int G, int K, int U, typename Cfg, bool BIAS>
+// PEER: sources may live on other ranks (owner << shift | row).  A template flag because the run-time test costs ~20
+// predicated instructions per gathered row in both modes.
+template <typename T, int VEC, int G, int K, int U, typename Cfg, bool BIAS, bool PEER = false>
 __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_rows_tiled(const KParams p) {
   static_assert(U <= G && G % U == 0, "a batch must not straddle column blocks");
   constexpr int RPW = 32 / G;                            // rows per step
@@ -87,6 +111,8 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
   const int gbase = grp * G;
   const long long n_slots = p.row_ids ? p.n_row_ids : p.n_rows;
   const long long s0 = ((long long)blockIdx.x * (kTiledThreads / 32) + (threadIdx.x >> 5)) * TR;
+  __shared__ float4 s_scale_lut[kScaleLut];
+  fill_scale_lut(s_scale_lut, p, threadIdx.x, kTiledThreads);
   if (s0 >= n_slots) return;   // warp-uniform
 
   // tile metadata: one slot per lane.  dg: in-degree, -1 = nothing to do here (padding slot or split row)
@@ -124,7 +150,7 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
     if (u < d) {
 #pragma unroll
       for (int k = 0; k < K; ++k)
-        if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(gathered_row<T>(p, src) + fm.f[k]);
+        if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw((PEER ? gathered_row<T>(p, src) : local_row<T>(p, src)) + fm.f[k]);
     }
   }
 
@@ -178,7 +204,7 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
         if (eb + u < d) {
 #pragma unroll
           for (int k = 0; k < K; ++k)
-            if (fm.ok[k]) r2[u][k] = Io<T, VEC>::load_raw(gathered_row<T>(p, src) + fm.f[k]);
+            if (fm.ok[k]) r2[u][k] = Io<T, VEC>::load_raw((PEER ? gathered_row<T>(p, src) : local_row<T>(p, src)) + fm.f[k]);
         }
       }
 #pragma unroll
@@ -207,10 +233,10 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
       if (u < dN) {
 #pragma unroll
         for (int k = 0; k < K; ++k)
-          if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw(gathered_row<T>(p, src) + fm.f[k]);
+          if (fm.ok[k]) raw[u][k] = Io<T, VEC>::load_raw((PEER ? gathered_row<T>(p, src) : local_row<T>(p, src)) + fm.f[k]);
       }
     }
-    if (deg >= 0) finalize_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, acc);
+    if (deg >= 0) finalize_row_ds<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, scales_of_row(s_scale_lut, p, row, deg), acc);
 
     row = rowN; beg = begN; deg = degN; d = dN; cv = cvN;
     if (has_bias) {
@@ -232,7 +258,6 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks(VEC, K)) k_row
 // Gather latency is hidden by bytes in flight in shared memory instead of by registers or by more warps:
 // 24 warps x 8 KB per SM versus 24 warps x 4 x 512 B with register staging.
 constexpr int kStreamThreads = 128;
-constexpr int kScaleLut = 256;       // in-degrees with precomputed scaler factors (rows at/above it: computed per row)
 
 __device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -275,7 +300,10 @@ __device__ __forceinline__ typename Io<T, VEC>::Raw lds_raw(unsigned addr) {
 }
 
 #ifndef PNA_STREAM_HALF_BYTES
-#define PNA_STREAM_HALF_BYTES 4096   // bytes of neighbour rows per ring half per warp
+#define PNA_STREAM_HALF_BYTES 4096   // bytes of neighbour rows per ring segment per warp
+#endif
+#ifndef PNA_STREAM_STAGES
+#define PNA_STREAM_STAGES 2          // ring segments per warp: one being reduced, the others in flight
 #endif
 // DEPTH scales the ring: 1 for local HBM gathers; 2 when remote rows arrive over NVLink (2-3x the latency, and a row
 // at the head of the in-order ring blocks the rows behind it)
@@ -284,14 +312,26 @@ struct StreamGeom {
   static constexpr int kBlockBytes = 32 * VEC * K * (int)sizeof(T);            // bytes of one ring slot
   static constexpr int kHalf = PNA_STREAM_HALF_BYTES * DEPTH;
   static constexpr int kH = (kHalf / kBlockBytes) < 4 ? 4 : ((kHalf / kBlockBytes) > 32 ? 32 : (kHalf / kBlockBytes));
-  static constexpr int kWarpBytes = 2 * kH * kBlockBytes;                        // two halves
+  static constexpr int kStages = PNA_STREAM_STAGES;                              // ring segments ("halves") per warp
+  static constexpr int kWarpBytes = kStages * kH * kBlockBytes;
   static constexpr size_t kSmem = 128 + (size_t)(kStreamThreads / 32) * kWarpBytes;
 };
 
 // 16-byte async copy global -> shared (LDGSTS, L2-only caching) with an L2 eviction-priority hint
+// PNA_STREAM_L1 = 1: the copy allocates in L1 (cp.async.ca) -- a source row that many destinations of the same SM gather
+// (power-law graphs: a handful of rows receive a third of all gathers) is then served by the SM's own L1 instead of the
+// one or two L2 slices that hold its lines, whose bandwidth is what bounds such graphs otherwise.
+#ifndef PNA_STREAM_L1
+#define PNA_STREAM_L1 0
+#endif
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src, unsigned long long policy) {
+#if PNA_STREAM_L1
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "l"(policy)
+               : "memory");
+#else
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "l"(policy)
                : "memory");
+#endif
 }
 // 8-byte variant (feature-split passes: 64-bit chunks per lane); .ca is the only qualifier cp.async allows below 16 bytes
 __device__ __forceinline__ void cp_async8(unsigned dst, const void* src, unsigned long long policy) {
@@ -431,19 +471,15 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   constexpr int G = 32;
   constexpr int H = StreamGeom<T, VEC, K, DEPTH>::kH;
   constexpr int SLOT = StreamGeom<T, VEC, K, DEPTH>::kBlockBytes;
+  constexpr int NST = StreamGeom<T, VEC, K, DEPTH>::kStages;
+  static_assert(!PNA_STREAM_TMA || NST == 2, "the bulk-copy build variant keeps the two-segment ring");
   constexpr unsigned FULL = 0xffffffffu;
   constexpr bool PEER = DEPTH > 1;     // the deep-ring instantiations are the ones launched with peer pointers
   extern __shared__ __align__(128) unsigned char smem[];
-  // degree-scaler factors of every in-degree below kScaleLut: one shared-memory read per row instead of logf + two IEEE
-  // divisions per lane per row (the same device function fills the table, so the factors keep their bits)
   __shared__ float4 s_scale_lut[kScaleLut];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < kScaleLut; i += kStreamThreads) {
-    const DegScales dsi = deg_scales(i, p.avg_log, p.avg_lin);
-    s_scale_lut[i] = make_float4(dsi.amp, dsi.att, dsi.lin, dsi.ilin);
-  }
-  __syncthreads();
+  fill_scale_lut(s_scale_lut, p, threadIdx.x, kStreamThreads);
 
   // this warp's rows: a contiguous range of the light view, cut at equal-cost partition boundaries
   const long long W = (long long)gridDim.x * (kStreamThreads / 32);
@@ -492,11 +528,13 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
 #endif
   // issue the copies of half n (positions n*H .. n*H+H-1) whose sources were fetched one step earlier
 #if PNA_STREAM_TMA
-  auto issue_half = [&](int n, int src) {
-    const int nvalid = min(H, Te - n * H);
-    const unsigned bar = bar0 + (n & 1) * 8;
+  int tma_issued = 0;
+  auto issue_half = [&](int stage, int src) {
+    const int nvalid = min(H, Te - tma_issued * H);
+    ++tma_issued;
+    const unsigned bar = bar0 + stage * 8;
     if (lane == 0) mbar_expect_tx(bar, (unsigned)nvalid * copy_bytes);
-    if (src >= 0) bulk_g2s(ring + ((n & 1) * H + lane) * SLOT, gathered_row<T>(p, src) + fblock, copy_bytes, bar);
+    if (src >= 0) bulk_g2s(ring + (stage * H + lane) * SLOT, gathered_row<T>(p, src) + fblock, copy_bytes, bar);
   };
 #else
   // every lane copies ITS OWN 16-byte chunk(s) of each neighbour row, and later reads exactly those bytes back:
@@ -505,8 +543,8 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   // byte address of this lane's chunk in row 0; a row is one unsigned 32 x 32 -> 64-bit multiply-add away (IMAD.WIDE.U32)
   const char* const xlane = reinterpret_cast<const char*>(static_cast<const T*>(p.x) + lane_elems);
   const unsigned ldxb = (unsigned)p.ldx * (unsigned)sizeof(T);
-  auto issue_half = [&](int n, int src) {
-    unsigned dst = ring + (unsigned)((n & 1) * H) * SLOT + lane * CB;
+  auto issue_half = [&](int stage, int src) {
+    unsigned dst = ring + (unsigned)(stage * H) * SLOT + lane * CB;
 #pragma unroll
     for (int u = 0; u < H; ++u, dst += SLOT) {
       const int s_u = __shfl_sync(FULL, src, u);
@@ -521,22 +559,31 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   };
 #endif
 
-  int pend = source_of(lane);                 // sources of half 0
+  int pend = source_of(lane);                 // sources of segment 0
   unsigned phase0 = 0, phase1 = 0;
   (void)phase0; (void)phase1;
   if (Te > 0) {
+#if PNA_STREAM_TMA
     issue_half(0, pend);
     pend = source_of(H + lane);
-#if PNA_STREAM_TMA
     if (H < Te) {
       issue_half(1, pend);
       pend = source_of(2 * H + lane);
     }
 #else
-    issue_half(1, pend);                      // possibly empty: keeps "one group per half" so wait_group<1> is exact
-    pend = source_of(2 * H + lane);
+    // fill the whole ring; segments past the end of the stream are copied too (row 0, never read): "one group per
+    // segment" keeps wait_group<NST-1> exact
+#pragma unroll
+    for (int s0 = 0; s0 < NST; ++s0) {
+      issue_half(s0, pend);
+      pend = source_of((s0 + 1) * H + lane);
+    }
 #endif
   }
+  IsoVals<Cfg> iso_vals;
+  if constexpr (Cfg::kStatic) iso_vals.init(p);
+  int stage = 0;        // ring segment that holds stream positions [n*H, n*H + H) being consumed
+  int n_issued = NST;   // segments issued so far
 
   // row metadata, 32 rows at a time, the next 32 prefetched while the current ones are reduced
   auto load_deg = [&](int r) -> int { return (r + lane < pb) ? __ldg(p.ldeg + r + lane) : -1; };
@@ -575,17 +622,16 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
       while (left > 0) {
         // segment = slots of this row inside the current half
         const int inhalf = q & (H - 1);
-        const int n = q / H;     // H is a power of two
-        if (inhalf == 0) {       // entering half n: wait for its copies
+        if (inhalf == 0) {       // entering a segment: wait for its copies
 #if PNA_STREAM_TMA
-          if (n & 1) { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
+          if (stage) { mbar_wait(bar0 + 8, phase1); phase1 ^= 1; }
           else { mbar_wait(bar0, phase0); phase0 ^= 1; }
 #else
-          cp_async_wait<1>();    // all groups but the newest (the other half) have landed
+          cp_async_wait<NST - 1>();    // all groups but the NST-1 newest (the segments still in flight) have landed
 #endif
         }
         const int seg = min(left, H - inhalf);
-        unsigned sp = ring + (unsigned)((n & 1) * H + inhalf) * SLOT + lane_off;
+        unsigned sp = ring + (unsigned)(stage * H + inhalf) * SLOT + lane_off;
         int t = 0;
         for (; t + 2 <= seg; t += 2, sp += 2 * SLOT) {      // two slots per step: FADD2/FMUL2 + FMNMX3
 #pragma unroll
@@ -610,32 +656,26 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
         }
         q += seg;
         left -= seg;
-        if ((q & (H - 1)) == 0 || q == Te) {   // half n fully consumed: refill it with half n+2
+        if ((q & (H - 1)) == 0 || q == Te) {   // segment fully consumed: refill it with the segment NST further on
 #if PNA_STREAM_TMA
           __syncwarp();
-          if ((n + 2) * H < Te) {
-            issue_half(n + 2, pend);
-            pend = source_of((n + 3) * H + lane);
+          if (n_issued * H < Te) {
+            issue_half(stage, pend);
+            pend = source_of((n_issued + 1) * H + lane);
           }
 #else
-          issue_half(n + 2, pend);             // empty group past the end of the stream
-          pend = source_of((n + 3) * H + lane);
+          issue_half(stage, pend);             // (a group of unread copies past the end of the stream)
+          pend = source_of((n_issued + 1) * H + lane);
 #endif
+          ++n_issued;
+          stage = (stage + 1 == NST) ? 0 : stage + 1;
         }
       }
       if (!chunk_row) {
-        if (deg == 0 && !p.sdeg) {
-          finalize_isolated_row<T, VEC, G, K, Cfg>(p, fm, (long long)row);
+        if (Cfg::kStatic && deg == 0 && !p.sdeg) {      // (the dynamic-configuration kernels keep one epilogue)
+          finalize_isolated_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, iso_vals);
         } else {
-          DegScales ds;
-          const int sd = p.sdeg ? __ldg(p.sdeg + row) : deg;      // the scalers' degree may be supplied separately (dense layer)
-          if (sd < kScaleLut) {
-            const float4 t = s_scale_lut[sd];
-            ds.amp = t.x; ds.att = t.y; ds.lin = t.z; ds.ilin = t.w;
-          } else {
-            ds = deg_scales(sd, p.avg_log, p.avg_lin);
-          }
-          finalize_row_ds<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, ds, acc);
+          finalize_row_ds<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, scales_of_row(s_scale_lut, p, row, deg), acc);
         }
       } else {
         float* __restrict__ part = p.partials + (long long)(row - (int)p.n_rows) * 4ll * p.F;
@@ -731,12 +771,20 @@ __global__ void __launch_bounds__(128) k_hub_tree(const KParams p, long long S) 
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       if (!fm.ok[k]) continue;
+      float* const dst[4] = {a[k].sum, a[k].sq, a[k].mn, a[k].mx};
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        a[k].sum[i] = __ldcg(part + 0ll * p.F + fm.f[k] + i);
-        a[k].sq[i] = __ldcg(part + 1ll * p.F + fm.f[k] + i);
-        a[k].mn[i] = __ldcg(part + 2ll * p.F + fm.f[k] + i);
-        a[k].mx[i] = __ldcg(part + 3ll * p.F + fm.f[k] + i);
+      for (int q = 0; q < 4; ++q) {
+        const float* src = part + (long long)q * p.F + fm.f[k];
+        if constexpr (VEC % 4 == 0) {
+#pragma unroll
+          for (int i = 0; i < VEC; i += 4) {
+            const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + i));
+            dst[q][i] = t4.x; dst[q][i + 1] = t4.y; dst[q][i + 2] = t4.z; dst[q][i + 3] = t4.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) dst[q][i] = __ldcg(src + i);
+        }
       }
     }
   };
@@ -753,32 +801,41 @@ __global__ void __launch_bounds__(128) k_hub_tree(const KParams p, long long S) 
   };
   Acc<VEC> acc[K];
   long long cur = -1;
-#pragma unroll 1
-  for (int j = 1; j < kTreeR; j += 2) {
-    const long long h0 = __shfl_sync(FULL, my_head, j);
-    const long long h1 = (j + 1 < kTreeR) ? __shfl_sync(FULL, my_head, j + 1) : -1;
-    if (h0 < 0 && h1 < 0) continue;
-    Acc<VEC> t0[K], t1[K];
-    if (h0 >= 0) load(base + (long long)j * S, t0);          // both loads in flight before the dependent adds
-    if (h1 >= 0) load(base + (long long)(j + 1) * S, t1);
-    auto fold = [&](long long head, const Acc<VEC> (&t)[K]) {
-      if (head != cur) {
-        if (cur >= 0) store(cur, acc);
-        load(head, acc);
-        cur = head;
+  auto fold = [&](long long head, const Acc<VEC> (&t)[K]) {
+    if (head != cur) {
+      if (cur >= 0) store(cur, acc);
+      load(head, acc);
+      cur = head;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        acc[k].sum[i] = __fadd_rn(acc[k].sum[i], t[k].sum[i]);
+        acc[k].sq[i] = __fadd_rn(acc[k].sq[i], t[k].sq[i]);
+        acc[k].mn[i] = fminf(acc[k].mn[i], t[k].mn[i]);
+        acc[k].mx[i] = fmaxf(acc[k].mx[i], t[k].mx[i]);
       }
+  };
+  // UB partials are requested before the first dependent add: the walk is a chain of L2 round trips, UB of them overlap
+  constexpr int UB = (K * VEC >= 16) ? 2 : 4;
+#pragma unroll 1
+  for (int j = 1; j < kTreeR; j += UB) {
+    long long hd[UB];
+    bool any = false;
 #pragma unroll
-      for (int k = 0; k < K; ++k)
+    for (int u = 0; u < UB; ++u) {
+      hd[u] = (j + u < kTreeR) ? __shfl_sync(FULL, my_head, (j + u) & 31) : -1;
+      any |= hd[u] >= 0;
+    }
+    if (!any) continue;
+    Acc<VEC> t[UB][K];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          acc[k].sum[i] = __fadd_rn(acc[k].sum[i], t[k].sum[i]);
-          acc[k].sq[i] = __fadd_rn(acc[k].sq[i], t[k].sq[i]);
-          acc[k].mn[i] = fminf(acc[k].mn[i], t[k].mn[i]);
-          acc[k].mx[i] = fmaxf(acc[k].mx[i], t[k].mx[i]);
-        }
-    };
-    if (h0 >= 0) fold(h0, t0);
-    if (h1 >= 0) fold(h1, t1);
+    for (int u = 0; u < UB; ++u)
+      if (hd[u] >= 0) load(base + (long long)(j + u) * S, t[u]);
+#pragma unroll
+    for (int u = 0; u < UB; ++u)
+      if (hd[u] >= 0) fold(hd[u], t[u]);
   }
   if (cur >= 0) store(cur, acc);
 }
@@ -926,7 +983,10 @@ static int launch_config(const KParams& p_in, cudaStream_t st) {
         PNA_REQUIRE(gt <= 0x7fffffffll, PNA_ERR_UNSUPPORTED, "too many rows for one launch: %lld", slots);
         const dim3 grid((unsigned)gt, gy);
         const bool b = p.bias != nullptr;
-        if (cfg == 1 && !b) k_rows_tiled<T, VEC, G, K, U, CfgMeanMaxMinStd, false><<<grid, kTiledThreads, 0, st>>>(p);
+        if (p.peer_x != nullptr) {   // narrow rows gathered over NVLink: the dynamic-configuration kernels only
+          if (!b) k_rows_tiled<T, VEC, G, K, U, CfgDynamic, false, true><<<grid, kTiledThreads, 0, st>>>(p);
+          else k_rows_tiled<T, VEC, G, K, U, CfgDynamic, true, true><<<grid, kTiledThreads, 0, st>>>(p);
+        } else if (cfg == 1 && !b) k_rows_tiled<T, VEC, G, K, U, CfgMeanMaxMinStd, false><<<grid, kTiledThreads, 0, st>>>(p);
         else if (cfg == 1) k_rows_tiled<T, VEC, G, K, U, CfgMeanMaxMinStd, true><<<grid, kTiledThreads, 0, st>>>(p);
         else if (!b) k_rows_tiled<T, VEC, G, K, U, CfgDynamic, false><<<grid, kTiledThreads, 0, st>>>(p);
         else k_rows_tiled<T, VEC, G, K, U, CfgDynamic, true><<<grid, kTiledThreads, 0, st>>>(p);

@@ -33,6 +33,13 @@ def make(cfg):
     if cfg == "3f": return synth.zinc_like(dtype=torch.float32)[:2]
     if cfg == "4": return synth.superpixel_like()
     if cfg == "5": return synth.powerlaw()
+    if cfg == "5u":   # power-law destinations, UNIFORM sources: no hot source rows
+        ei, x = synth.powerlaw()
+        g = torch.Generator().manual_seed(5)
+        return torch.stack([torch.randint(0, x.size(0), (ei.size(1),), generator=g), ei[1]]), x
+    if cfg == "5w":   # the same rows with (almost) no edges: the write path alone
+        ei, x = synth.powerlaw()
+        return ei[:, :1000], x
     raise SystemExit("unknown config")
 
 
