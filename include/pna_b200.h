@@ -62,6 +62,10 @@ enum pna_flags {
                                   mean=min=max=0, std=sqrt(1e-5), then scaled. */
   PNA_FLAG_SKIP_LIGHT = 2u,    /* do not process rows below the split threshold (used to overlap halo exchange) */
   PNA_FLAG_SKIP_HUBS = 4u,     /* do not process rows at/above the split threshold */
+  PNA_FLAG_GATHER_L1 = 16u,    /* hint: a few source rows receive a large share of all gathers (power-law graphs).  The
+                                  gathered rows are then also kept in the SMs' L1, so a hot row is not served by the few L2
+                                  slices that hold its lines.  Without hot sources the hint costs a few percent.  Honoured by
+                                  the streamed kernel for the reference configs' aggregator / scaler lists. */
   PNA_FLAG_RELU_VAR = 8u       /* the "var" aggregator is clamped at 0 (models/dgl/aggregators.py:22-26 and
                                   models/pytorch/pna/aggregators.py:63-76 apply torch.relu; the PyG flavour,
                                   models/pytorch_geometric/aggregators.py:25-28, does not); its gradient is masked where
@@ -119,6 +123,10 @@ typedef struct pna_csr {
   int64_t n_light_edges;    /* out (host): slots in the view (= n_edges when chunk rows are included) */
   int64_t n_src_nodes;      /* in: sources are validated against [0, n_src_nodes); 0 = n_nodes.  > n_nodes for the
                                destination-partitioned multi-GPU path, where sources index [local rows ; halo rows] */
+  float hot_source_fraction; /* out (host): estimated share of the gathers that go to frequent source rows (sampled: sources
+                                seen >= 4 times among 65 536 evenly spaced slots).  ~0 for citation / molecule / kNN graphs,
+                                ~0.9 for Zipf-distributed sources; above ~0.25 pass PNA_FLAG_GATHER_L1 to the aggregation */
+  int32_t reserved;
 } pna_csr_t;
 
 /* Bytes of device scratch pna_csr_build needs for (n_nodes, n_edges) on the current device. */

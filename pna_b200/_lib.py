@@ -32,7 +32,7 @@ PNA_OK = 0
 PNA_F32, PNA_BF16 = 0, 1
 AGGR_CODES = {"sum": 0, "mean": 1, "min": 2, "max": 3, "var": 4, "std": 5, "_skip": 15}
 SCALER_CODES = {"identity": 0, "amplification": 1, "attenuation": 2, "linear": 3, "inverse_linear": 4}
-FLAG_ZERO_ISOLATED, FLAG_SKIP_LIGHT, FLAG_SKIP_HUBS, FLAG_RELU_VAR = 1, 2, 4, 8
+FLAG_ZERO_ISOLATED, FLAG_SKIP_LIGHT, FLAG_SKIP_HUBS, FLAG_RELU_VAR, FLAG_GATHER_L1 = 1, 2, 4, 8, 16
 (QUERY_ABI_VERSION, QUERY_SM_ARCH, QUERY_DEFAULT_SPLIT, QUERY_DEFAULT_CHUNK, QUERY_DEVICE_SM_COUNT,
  QUERY_MAX_FEATURES, QUERY_SIZEOF_CSR, QUERY_SIZEOF_AGG) = range(8)
 
@@ -59,7 +59,7 @@ class CsrStruct(C.Structure):
         ("n_hubs", C.c_int64), ("n_chunks", C.c_int64),
         ("max_degree", C.c_int32), ("n_part", C.c_int32),
         ("light_rowptr", C.c_void_p), ("light_deg", C.c_void_p), ("light_col", C.c_void_p), ("part", C.c_void_p),
-        ("n_light_edges", C.c_int64), ("n_src_nodes", C.c_int64),
+        ("n_light_edges", C.c_int64), ("n_src_nodes", C.c_int64), ("hot_source_fraction", C.c_float), ("reserved", C.c_int32),
     ]
 
 

@@ -37,6 +37,9 @@ def _rows2d(t: torch.Tensor, what: str) -> torch.Tensor:
     return t
 
 
+HOT_SOURCE_FRACTION_FOR_L1 = 0.25      # CSRGraph.hot_source_fraction above which the gathers also allocate in L1
+
+
 def _check_scaler_degree(t: torch.Tensor, n_rows: int, dev) -> torch.Tensor:
     if t.dtype != torch.int32 or t.device != dev or t.numel() != n_rows or not t.is_contiguous():
         raise ValueError("scaler_degree must be a contiguous int32 [n_rows] tensor on the same device")
@@ -58,7 +61,7 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
                       messages_in_csr_order: bool = False, zero_isolated: bool = False, relu_var: bool = False,
                       out: Optional[torch.Tensor] = None, row_ids: Optional[torch.Tensor] = None,
                       skip_light: bool = False, skip_hubs: bool = False, view=None, peer=None,
-                      scaler_degree: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      scaler_degree: Optional[torch.Tensor] = None, gather_l1: Optional[bool] = None) -> torch.Tensor:
     """Run the CUDA aggregation (no autograd).  Returns ``[N, towers * (has_self + S*A) * Ft]``.
 
     gathered : [n_src, F] rows that are gathered through ``csr.col`` (x for PNAConvSimple; V = x W_j^T + b for
@@ -105,7 +108,10 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
     if row_ids is not None:
         if row_ids.dtype != torch.int32 or not row_ids.is_contiguous() or row_ids.device != dev:
             raise ValueError("row_ids must be a contiguous int32 tensor on the same device")
-    flags = (_lib.FLAG_ZERO_ISOLATED if zero_isolated else 0) | (_lib.FLAG_SKIP_LIGHT if skip_light else 0) | \
+    if gather_l1 is None:     # hot source rows (power-law graphs): keep gathered rows in L1 too (PNA_FLAG_GATHER_L1)
+        gather_l1 = (not messages_in_csr_order) and peer is None and csr.hot_source_fraction > HOT_SOURCE_FRACTION_FOR_L1
+    flags = (_lib.FLAG_GATHER_L1 if gather_l1 else 0) | \
+            (_lib.FLAG_ZERO_ISOLATED if zero_isolated else 0) | (_lib.FLAG_SKIP_LIGHT if skip_light else 0) | \
             (_lib.FLAG_SKIP_HUBS if skip_hubs else 0) | (_lib.FLAG_RELU_VAR if relu_var else 0)
     partials = None if skip_hubs else csr.hub_partials(F)
     d = _lib.AggStruct(

@@ -53,6 +53,7 @@ class CSRGraph:
     _partials: dict = field(default_factory=dict, repr=False)
     _deg: Optional[torch.Tensor] = field(default=None, repr=False)
     _dst: Optional[torch.Tensor] = field(default=None, repr=False)
+    hot_source_fraction: float = 0.0      # pna_csr_t.hot_source_fraction: share of the gathers going to frequent sources
 
     @property
     def device(self) -> torch.device:
@@ -176,7 +177,8 @@ def build_csr(src: torch.Tensor, dst: torch.Tensor, n_nodes: int, split_threshol
     return CSRGraph(n_nodes=N, n_edges=E, rowptr=rowptr, col=col, perm=perm, split_threshold=split, chunk_edges=chunk,
                     hub_info=hub_info[:nh].clone() if nh else hub_info[:0], chunk_items=chunk_items[:nc].clone() if nc else chunk_items[:0],
                     n_hubs=nh, n_chunks=nc, max_degree=int(st.max_degree), light_rowptr=light_rowptr, light_deg=light_deg,
-                    light_col=light_col, part=part, n_part=n_part, n_light_edges=int(st.n_light_edges))
+                    light_col=light_col, part=part, n_part=n_part, n_light_edges=int(st.n_light_edges),
+                    hot_source_fraction=float(st.hot_source_fraction))
 
 
 # ---- cache by graph identity ---------------------------------------------------------------------------------

@@ -278,37 +278,14 @@ struct SharedDivisor {
 // A row without in-edges (PyG semantics, aggregators.py:13-32 / scalers.py:8-29 at d = 0): mean = min = max = sum = var = 0,
 // std = sqrt(1e-5); amplification = log(1)/delta = 0, attenuation = linear-inverse = 1, linear = 0 -- every output segment is
 // one constant splat.  Power-law graphs consist mostly of such rows (94 % in config 5), so they get their own short path.
-// The constants of an isolated row: v[s][a] = scaler_s(0) * aggregator_a(empty neighbourhood).  Row independent, so a
-// persistent warp computes them once (IEEE division of deg_scales included) and an isolated row is stores only.
-template <typename Cfg>
-struct IsoVals {
-  float v[Cfg::NS][Cfg::NA];
-  __device__ __forceinline__ void init(const KParams& p) {
-    const int nA = Cfg::kStatic ? Cfg::NA : p.nA, nS = Cfg::kStatic ? Cfg::NS : p.nS;
-    const unsigned acodes = Cfg::kStatic ? Cfg::ACODES : p.acodes, scodes = Cfg::kStatic ? Cfg::SCODES : p.scodes;
-    const bool zero_all = (p.flags & PNA_FLAG_ZERO_ISOLATED) != 0;
-    const float sd0 = __fsqrt_rn(__fadd_rn(0.0f, 1e-5f));
-    const DegScales ds = deg_scales(0, p.avg_log, p.avg_lin);
-#pragma unroll
-    for (int s = 0; s < Cfg::NS; ++s)
-#pragma unroll
-      for (int a = 0; a < Cfg::NA; ++a) {
-        float r = 0.0f;
-        if (s < nS && a < nA) {
-          const unsigned ac = (acodes >> (4 * a)) & 15u, sc = (scodes >> (4 * s)) & 15u;
-          const float base = (ac == PNA_AGGR_STD && !zero_all) ? sd0 : 0.0f;
-          r = (sc == PNA_SCALE_IDENTITY) ? base : __fmul_rn(base, ds.of(sc));
-        }
-        v[s][a] = r;
-      }
-  }
-};
-
+// `ds0` = the scaler factors of in-degree 0 (from the kernel's shared-memory table: no division on this path).
 template <typename T, int VEC, int G, int K, typename Cfg>
 __device__ __forceinline__ void finalize_isolated_row(const KParams& p, const FeatMap<VEC, G, K>& fm, long long row,
-                                                      const IsoVals<Cfg>& iv) {
+                                                      const DegScales& ds0) {
   const int nA = Cfg::kStatic ? Cfg::NA : p.nA, nS = Cfg::kStatic ? Cfg::NS : p.nS;
-  const unsigned acodes = Cfg::kStatic ? Cfg::ACODES : p.acodes;
+  const unsigned acodes = Cfg::kStatic ? Cfg::ACODES : p.acodes, scodes = Cfg::kStatic ? Cfg::SCODES : p.scodes;
+  const bool zero_all = (p.flags & PNA_FLAG_ZERO_ISOLATED) != 0;
+  const float sd0 = __fsqrt_rn(__fadd_rn(0.0f, 1e-5f));      // constant-folded
   T* __restrict__ orow = static_cast<T*>(p.out) + row * p.ldo;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -324,12 +301,15 @@ __device__ __forceinline__ void finalize_isolated_row(const KParams& p, const Fe
       if (!Cfg::kStatic && a >= nA) break;
       const unsigned ac = (acodes >> (4 * a)) & 15u;
       if (ac == PNA_AGGR_SKIP) continue;
+      const float base = (ac == PNA_AGGR_STD && !zero_all) ? sd0 : 0.0f;
 #pragma unroll
       for (int s = 0; s < Cfg::NS; ++s) {
         if (!Cfg::kStatic && s >= nS) break;
+        const unsigned sc = (scodes >> (4 * s)) & 15u;
+        const float v = (sc == PNA_SCALE_IDENTITY) ? base : __fmul_rn(base, ds0.of(sc));
         float o[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = iv.v[s][a];
+        for (int i = 0; i < VEC; ++i) o[i] = v;
         Io<T, VEC>::store(obase + (s * nA + a) * p.Ft, o);
       }
     }

@@ -318,29 +318,28 @@ struct StreamGeom {
 };
 
 // 16-byte async copy global -> shared (LDGSTS, L2-only caching) with an L2 eviction-priority hint
-// PNA_STREAM_L1 = 1: the copy allocates in L1 (cp.async.ca) -- a source row that many destinations of the same SM gather
-// (power-law graphs: a handful of rows receive a third of all gathers) is then served by the SM's own L1 instead of the
-// one or two L2 slices that hold its lines, whose bandwidth is what bounds such graphs otherwise.
-#ifndef PNA_STREAM_L1
-#define PNA_STREAM_L1 0
-#endif
+// L1 = true: the copy allocates in L1 (cp.async.ca).  A source row that many destinations of the same SM gather (power-law
+// graphs: a handful of rows receive a third of all gathers) is then served by the SM's own L1 instead of the few L2 slices
+// that hold its lines -- their bandwidth (about 1 TB/s for a 1 KB row) is what bounds such graphs otherwise: config-5 share
+// 4.57 -> 3.34 ms.  For graphs without hot sources the L1 detour costs (config 2: 0.277 -> 0.293 ms), hence a mode the
+// caller selects (PNA_FLAG_GATHER_L1), not a default.
+template <bool L1 = false>
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src, unsigned long long policy) {
-#if PNA_STREAM_L1
-  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "l"(policy)
-               : "memory");
-#else
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "l"(policy)
-               : "memory");
-#endif
+  if constexpr (L1)
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "l"(policy)
+                 : "memory");
+  else
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "l"(policy)
+                 : "memory");
 }
 // 8-byte variant (feature-split passes: 64-bit chunks per lane); .ca is the only qualifier cp.async allows below 16 bytes
 __device__ __forceinline__ void cp_async8(unsigned dst, const void* src, unsigned long long policy) {
   asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dst), "l"(__cvta_generic_to_global(src)), "l"(policy)
                : "memory");
 }
-template <int BYTES>
+template <int BYTES, bool L1 = false>
 __device__ __forceinline__ void cp_async_chunk(unsigned dst, const void* src, unsigned long long policy) {
-  if constexpr (BYTES == 16) cp_async16(dst, src, policy); else cp_async8(dst, src, policy);
+  if constexpr (BYTES == 16) cp_async16<L1>(dst, src, policy); else cp_async8(dst, src, policy);
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -466,7 +465,7 @@ __device__ __noinline__ void fold_split_row(const KParams& p, int c, int fblock)
   finalize_row<T, VEC, G, K, Cfg>(p, fm, (long long)__ldg(p.hub_info + 4 * h), __ldg(p.hub_info + 4 * h + 3), acc);
 }
 
-template <typename T, int VEC, int K, typename Cfg, bool BIAS, int DEPTH, bool FOLD = false>
+template <typename T, int VEC, int K, typename Cfg, bool BIAS, int DEPTH, bool FOLD = false, bool L1 = false>
 __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_rows_stream(const __grid_constant__ KParams p) {
   constexpr int G = 32;
   constexpr int H = StreamGeom<T, VEC, K, DEPTH>::kH;
@@ -553,7 +552,7 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
       else sp = xlane + (unsigned long long)(unsigned)s_u * ldxb;
 #pragma unroll
       for (int k = 0; k < K; ++k)
-        if (fm.ok[k]) cp_async_chunk<CB>(dst + k * (32 * CB), sp + k * (32 * CB), keep);
+        if (fm.ok[k]) cp_async_chunk<CB, L1>(dst + k * (32 * CB), sp + k * (32 * CB), keep);
     }
     cp_async_commit();
   };
@@ -580,8 +579,6 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
     }
 #endif
   }
-  IsoVals<Cfg> iso_vals;
-  if constexpr (Cfg::kStatic) iso_vals.init(p);
   int stage = 0;        // ring segment that holds stream positions [n*H, n*H + H) being consumed
   int n_issued = NST;   // segments issued so far
 
@@ -673,7 +670,7 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
       }
       if (!chunk_row) {
         if (Cfg::kStatic && deg == 0 && !p.sdeg) {      // (the dynamic-configuration kernels keep one epilogue)
-          finalize_isolated_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, iso_vals);
+          finalize_isolated_row<T, VEC, G, K, Cfg>(p, fm, (long long)row, scales_of_row(s_scale_lut, p, row, 0));
         } else {
           finalize_row_ds<T, VEC, G, K, Cfg>(p, fm, (long long)row, deg, scales_of_row(s_scale_lut, p, row, deg), acc);
         }
@@ -936,10 +933,11 @@ static int launch_config(const KParams& p_in, cudaStream_t st) {
         // streamed gather over the light view, persistent warps
         const bool b = p.bias != nullptr;
         const bool deep = p.peer_x != nullptr;
-#define PNA_LAUNCH_STREAM_(CFG, B, DEPTH, FOLD)                                                                         \
+#define PNA_LAUNCH_STREAM_(CFG, B, DEPTH, FOLD) PNA_LAUNCH_STREAM__(CFG, B, DEPTH, FOLD, false)
+#define PNA_LAUNCH_STREAM__(CFG, B, DEPTH, FOLD, L1)                                                                    \
   do {                                                                                                             \
     constexpr size_t smem = StreamGeom<T, VEC, K, DEPTH>::kSmem;                                                   \
-    auto kern = k_rows_stream<T, VEC, K, CFG, B, DEPTH, FOLD>;                                                         \
+    auto kern = k_rows_stream<T, VEC, K, CFG, B, DEPTH, FOLD, L1>;                                                     \
     static int resident = 0;  /* CTAs of this kernel that fit the device (all B200s alike) */                     \
     if (resident == 0) {                                                                                           \
       if (smem > 48 * 1024) PNA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -965,6 +963,12 @@ static int launch_config(const KParams& p_in, cudaStream_t st) {
           if (cfg == 1 && !b) PNA_LAUNCH_STREAM_(CfgMeanMaxMinStd, false, 2, false);
           else if (!b) PNA_LAUNCH_STREAM_(CfgDynamic, false, 2, false);
           else PNA_LAUNCH_STREAM_(CfgDynamic, true, 2, false);
+        } else if ((p.flags & PNA_FLAG_GATHER_L1) && cfg == 1 && !b) {      // hot source rows: L1-allocating copies
+          p.hub_done = nullptr;
+          PNA_LAUNCH_STREAM__(CfgMeanMaxMinStd, false, 1, false, true);
+        } else if ((p.flags & PNA_FLAG_GATHER_L1) && cfg == 2 && !b) {
+          p.hub_done = nullptr;
+          PNA_LAUNCH_STREAM__(CfgMeanMaxMinStdId, false, 1, false, true);
         } else if (cfg == 1 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, false);
         else if (cfg == 1) PNA_LAUNCH_STREAM(CfgMeanMaxMinStd, true);
         else if (cfg == 2 && !b) PNA_LAUNCH_STREAM(CfgMeanMaxMinStdId, false);
@@ -974,6 +978,7 @@ static int launch_config(const KParams& p_in, cudaStream_t st) {
         folded = chunks_in_stream && p.hub_done != nullptr;
 #undef PNA_LAUNCH_STREAM
 #undef PNA_LAUNCH_STREAM_
+#undef PNA_LAUNCH_STREAM__
        }
       } else if constexpr (G >= U && G % U == 0) {
         constexpr int TR = (8 * RPW < 32) ? 8 * RPW : 32;

@@ -12,8 +12,27 @@
 namespace pna {
 
 struct Counters {  // device-side, copied back once at the end of the build
-  int n_hubs, n_chunks, max_degree, err;
+  int n_hubs, n_chunks, max_degree, err, hot;
 };
+
+// ---- share of the gathers that go to frequent source rows (decides PNA_FLAG_GATHER_L1) ---------------------------------------
+// n_sample evenly spaced CSR slots are counted into a small hash table; a sampled slot is "hot" when its source was seen at
+// least 4 times, i.e. receives more than about E / (n_sample / 4) gathers.  An estimate: collisions and sampling noise move it
+// by a percent, the graphs it has to tell apart differ by 0.9.
+__device__ __forceinline__ unsigned hot_hash(int v, unsigned mask) { return ((unsigned)v * 2654435761u >> 7) & mask; }
+__global__ void k_hot_count(const int* __restrict__ col, long long E, int n_sample, unsigned mask, int* __restrict__ table) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sample) return;
+  atomicAdd(table + hot_hash(__ldg(col + (long long)i * (E / n_sample)), mask), 1);
+}
+__global__ void k_hot_sum(const int* __restrict__ col, long long E, int n_sample, unsigned mask, const int* __restrict__ table,
+                          Counters* ctr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int hot = 0;
+  if (i < n_sample) hot = table[hot_hash(__ldg(col + (long long)i * (E / n_sample)), mask)] >= 4;
+  const unsigned m = __ballot_sync(0xffffffffu, hot);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&ctr->hot, __popc(m));
+}
 
 __global__ void k_prepare_keys(const long long* __restrict__ src, const long long* __restrict__ dst, int E, long long N,
                                long long NS, int* __restrict__ keys, int* __restrict__ vals, Counters* ctr) {
@@ -295,6 +314,17 @@ extern "C" int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* 
       PNA_CUDA_TRY(cudaGetLastError());
     }
   }
+  // hot-source estimate: keys_out is free once the row pointer exists; the table is the largest power of two it can hold
+  int n_sample = 0;
+  if (E >= 4096) {
+    n_sample = E < 65536 ? (int)E : 65536;
+    unsigned tsize = 131072;
+    while ((size_t)tsize * sizeof(int) > (size_t)E * sizeof(int)) tsize >>= 1;    // keys_out holds >= E ints
+    PNA_CUDA_TRY(cudaMemsetAsync(keys_out, 0, (size_t)tsize * sizeof(int), st));
+    k_hot_count<<<(unsigned)((n_sample + TB - 1) / TB), TB, 0, st>>>(csr->col, E, n_sample, tsize - 1, keys_out);
+    k_hot_sum<<<(unsigned)((n_sample + TB - 1) / TB), TB, 0, st>>>(csr->col, E, n_sample, tsize - 1, keys_out, ctr);
+    PNA_CUDA_TRY(cudaGetLastError());
+  }
   int n_light = 0;
   if (csr->light_rowptr) {   // light view (optional: all four arrays or none)
     PNA_REQUIRE(csr->light_deg && csr->part && (E == 0 || csr->light_col) && csr->n_part >= 1, PNA_ERR_BAD_ARG,
@@ -316,5 +346,6 @@ extern "C" int pna_csr_build(const int64_t* src, const int64_t* dst, pna_csr_t* 
   csr->n_chunks = host.n_chunks;
   csr->max_degree = host.max_degree;
   csr->n_light_edges = n_light;
+  csr->hot_source_fraction = n_sample ? (float)host.hot / (float)n_sample : 0.0f;
   return PNA_OK;
 }

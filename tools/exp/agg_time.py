@@ -18,6 +18,14 @@ ap.add_argument("--once", action="store_true")
 ap.add_argument("--tag", default="")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
+if os.environ.get("PNA_EXP_L2_PERSIST_MB"):     # experiment: L2 set-aside for persisting (evict_last) lines
+    import ctypes
+    torch.cuda.init(); torch.zeros(1, device=dev)
+    rt = ctypes.CDLL("libcudart.so.12")
+    mb = int(os.environ["PNA_EXP_L2_PERSIST_MB"])
+    rc = rt.cudaDeviceSetLimit(6, ctypes.c_size_t(mb << 20))      # cudaLimitPersistingL2CacheSize
+    got = ctypes.c_size_t(0); rt.cudaDeviceGetLimit(ctypes.byref(got), 6)
+    print(f"# persisting L2 limit: asked {mb} MiB rc {rc} -> {got.value >> 20} MiB", file=sys.stderr)
 peak = 6571.6
 pk = os.path.join(os.path.dirname(__file__), "..", "..", "MEASURED_PEAKS.json")
 if os.path.exists(pk):
