@@ -203,6 +203,33 @@ def side_configs(dev, flush, steps, peak):
     measure("configs[2]", ei[0], ei[1], x, lambda idx: x[idx], "ZINC-shaped batch: 12 000 molecule-like graphs, F=75 bf16 (150-byte rows)",
             x.size(0))
 
+    # the ZINC-shaped full layer (realworld_benchmark/configs: towers=5, 75 -> 75): PNAConv forward, fp32, CSR cached
+    ei32, x32, _ = synth.zinc_like(dtype=torch.float32)
+    degh = synth.degree_histogram(ei32[1], x32.size(0))
+    torch.manual_seed(0)
+    refl = O.PNAConvOracle(75, 75, AGGRS, SCALERS, degh, towers=5, divide_input=True)
+    layl = pna_b200.PNAConv(75, 75, AGGRS, SCALERS, degh, towers=5, divide_input=True)
+    layl.load_state_dict(refl.state_dict())
+    layl = layl.to(dev)
+    xl, eil = x32.to(dev), ei32.to(dev)
+    csrl = pna_b200.build_csr(eil[0], eil[1], x32.size(0))
+    with torch.no_grad():
+        wantl = refl(x32, ei32)
+        gotl = layl(xl, eil, csr=csrl)
+        for _ in range(3):
+            layl(xl, eil, csr=csrl)
+        s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(20):
+            layl(xl, eil, csr=csrl)
+        t_.record(); torch.cuda.synchronize()
+    res["configs[2] layer"] = {"workload": "ZINC-shaped batch, PNAConv(75, 75, towers=5, divide_input=True) forward, fp32, CSR cached",
+                               "n_nodes": x32.size(0), "n_edges": ei32.size(1), "ms": s_.elapsed_time(t_) / 20,
+                               "edges_per_s": ei32.size(1) / (s_.elapsed_time(t_) / 20 * 1e-3),
+                               "max_abs_err_vs_cpu_reference": float((gotl.cpu() - wantl).abs().max())}
+    del xl, eil, csrl, layl, gotl
+    torch.cuda.empty_cache()
+
     # configs[3], one GPU's share: 15 000 superpixel graphs, F = 64
     ei = synth.superpixel_shard(0, 15_000, dev)
     n4 = 15_000 * 70

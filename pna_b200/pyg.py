@@ -16,7 +16,7 @@ from torch.nn import Linear, Module, ModuleList, ReLU, Sequential
 from . import padding as pad
 from .aggregate import avg_deg_from_histogram, pna_aggregate, row_scales
 from .linear import compact_path_ok, post_linear, post_linear_scaled
-from .csr import CSRGraph, csr_from_edge_index
+from .csr import CSRGraph, csr_from_edge_index, tensor_version
 
 _AGGRS = ("sum", "mean", "min", "max", "var", "std")          # aggregators.py:35-42
 _SCALERS = ("identity", "amplification", "attenuation", "linear", "inverse_linear")  # scalers.py:32-38
@@ -211,22 +211,45 @@ class PNAConv(Module):
             _reset(nn)
         self.lin.reset_parameters()
 
-    # -- message side ---------------------------------------------------------------------------------------------
-    def _affine_terms(self, x: Tensor, Fp: int):
-        """U = x W_i^T (destination side), V = x W_j^T + b (source side), both [N, T*Fp]; Fp >= F_in pads every tower
-        block with zero features (zero weight rows: the GEMM writes them)."""
+    # -- weights in the layout the forward pass consumes ------------------------------------------------------------------
+    def _prepared(self, Fp: int):
+        """The towers' weights packed once per parameter version instead of once per call:
+          w_uv [2*T*Fp, in], b_uv  -- rows [0, T*Fp) give U = x W_i^T (destination side), rows [T*Fp, 2*T*Fp) give
+                                      V = x W_j^T + b (source side): ONE node-level GEMM for both (pna.py:94,147-149);
+                                      divide_input: tower t only sees its own F_in input columns (block-diagonal);
+          w_post [T, F_out, (1+S*A)*Fp], b_post [T, F_out] -- first post Linear of every tower with zero columns at the pad
+                                      positions: ONE batched GEMM over all towers (pna.py:132).
+        With autograd enabled the pack is rebuilt every call (it is part of the graph); otherwise it is cached."""
+        params = [p_ for nn in list(self.pre_nns) + list(self.post_nns) for p_ in nn[0].parameters()]
+        key = (Fp, tuple(tensor_version(p_) for p_ in params), tuple(p_.data_ptr() for p_ in params))
+        cache = torch.is_grad_enabled() is False or not any(p_.requires_grad for p_ in params)
+        if cache and getattr(self, "_prep", None) is not None and self._prep[0] == key:
+            return self._prep[1]
         T, Fi = self.towers, self.F_in
         Wi = [pad.expand_weight_rows(nn[0].weight[:, :Fi], Fi, Fp) for nn in self.pre_nns]
         Wj = [pad.expand_weight_rows(nn[0].weight[:, Fi:2 * Fi], Fi, Fp) for nn in self.pre_nns]
         b = torch.cat([torch.nn.functional.pad(nn[0].bias, (0, Fp - Fi)) for nn in self.pre_nns])
         if self.divide_input and T > 1:
-            # tower t only sees its own F_in input columns: block-diagonal [T*Fp, T*F_in] weight, one GEMM
-            U = x @ torch.block_diag(*Wi).t()
-            V = torch.addmm(b, x, torch.block_diag(*Wj).t())
+            w_uv = torch.cat([torch.block_diag(*Wi), torch.block_diag(*Wj)], 0)
         else:
-            U = x @ torch.cat(Wi, 0).t()
-            V = torch.addmm(b, x, torch.cat(Wj, 0).t())
-        return U, V
+            w_uv = torch.cat(Wi + Wj, 0)
+        b_uv = torch.cat([torch.zeros_like(b), b])
+        blocks = 1 + len(self.aggregators) * len(self.scalers)
+        w_post = torch.stack([pad.expand_weight_cols(nn[0].weight, blocks, Fi, Fp) for nn in self.post_nns])
+        b_post = torch.stack([nn[0].bias for nn in self.post_nns])
+        prep = (w_uv, b_uv, w_post, b_post)
+        if cache:
+            self._prep = (key, prep)
+        return prep
+
+    # -- message side ---------------------------------------------------------------------------------------------
+    def _affine_terms(self, x: Tensor, Fp: int):
+        """U = x W_i^T (destination side), V = x W_j^T + b (source side), both [N, T*Fp] -- two halves of one GEMM result;
+        Fp >= F_in pads every tower block with zero features (zero weight rows: the GEMM writes them)."""
+        w_uv, b_uv = self._prepared(Fp)[:2]
+        uv = torch.addmm(b_uv, x, w_uv.t())
+        h = uv.size(1) // 2
+        return uv[:, :h], uv[:, h:]
 
     def _messages_in_slot_order(self, x: Tensor, csr: CSRGraph, edge_attr: Optional[Tensor]) -> Tensor:
         """General path (edge features or pre_layers > 1): pna.py:137-150 evaluated on CSR-ordered edges."""
@@ -263,15 +286,19 @@ class PNAConv(Module):
             out = pna_aggregate(msgs, csr, self.aggregators, self.scalers, self.avg_deg, messages_in_csr_order=True,
                                 **common)
         out = out.view(x.size(0), T, -1)                       # [N, T, (1 + S*A) * Fp]  (pna.py:131)
-        blocks = 1 + len(self.aggregators) * len(self.scalers)
-        outs = []
-        for t, nn in enumerate(self.post_nns):
-            h = torch.nn.functional.linear(out[:, t], pad.expand_weight_cols(nn[0].weight, blocks, Fi, Fp), nn[0].bias)
-            for m in list(nn)[1:]:
-                h = m(h)
-            outs.append(h)
-        out = torch.cat(outs, dim=1) if T > 1 else outs[0]
+        w_post, b_post = self._prepared(Fp)[2:]
+        # first post Linear of all towers: one batched GEMM on the [N, T, W] view (tower = batch, no copy of the big tensor)
+        h = torch.baddbmm(b_post.unsqueeze(1), out.transpose(0, 1), w_post.transpose(1, 2))      # [T, N, F_out]
+        if len(self.post_nns[0]) > 1:
+            h = torch.stack([self._rest(nn, h[t]) for t, nn in enumerate(self.post_nns)])
+        out = h.transpose(0, 1).reshape(x.size(0), T * self.F_out) if T > 1 else h[0]
         return self.lin(out)
+
+    @staticmethod
+    def _rest(nn, h):
+        for m in list(nn)[1:]:
+            h = m(h)
+        return h
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels}, towers={self.towers})"
