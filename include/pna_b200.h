@@ -223,6 +223,11 @@ typedef struct pna_agg {
    * (models/pytorch/pna/scalers.py:13,21,28,35), and its max/min reduce over the other adjacency axis while still being
    * scaled with the row degree.  NULL: scalers use rowptr[i+1] - rowptr[i] (PyG / DGL). */
   const int32_t* scaler_degree;
+  /* optional: ONE int32 of device scratch (the library zeroes it on the stream before the launch).  When given, the streamed
+   * kernel deals out only the first 70 % of the row partitions statically and hands out the rest one at a time through
+   * this counter, so warps that finish their static range early take over work from slow ones.  Not to be shared by
+   * concurrent calls.  NULL: fully static assignment. */
+  int32_t* work_counter;
 } pna_agg_t;
 
 int pna_aggregate_fwd(const pna_agg_t* desc, pna_stream_t stream);

@@ -83,7 +83,7 @@ class AggStruct(C.Structure):
         ("row_ids", C.c_void_p), ("n_row_ids", C.c_int64),
         ("light_rowptr", C.c_void_p), ("light_deg", C.c_void_p), ("light_col", C.c_void_p), ("part", C.c_void_p),
         ("n_part", C.c_int32), ("n_view_rows", C.c_int64), ("peer_gathered", C.c_void_p), ("peer_shift", C.c_int32),
-        ("max_degree", C.c_int32), ("hub_done", C.c_void_p), ("scaler_degree", C.c_void_p),
+        ("max_degree", C.c_int32), ("hub_done", C.c_void_p), ("scaler_degree", C.c_void_p), ("work_counter", C.c_void_p),
     ]
 
 

@@ -40,6 +40,20 @@ def _rows2d(t: torch.Tensor, what: str) -> torch.Tensor:
 HOT_SOURCE_FRACTION_FOR_L1 = 0.25      # CSRGraph.hot_source_fraction above which the gathers also allocate in L1
 
 
+DYNAMIC_TAIL_MIN_PARTITION_COST = 256
+
+
+def _dynamic_tail(csr: CSRGraph) -> bool:
+    """Hand the last 30 % of the row partitions out dynamically (pna_agg_t.work_counter)?  Every grab restarts the warp's
+    gather ring (~6 us of serial latency: counter, partition bounds, first sources, first rows), so it pays only when a
+    partition is much more work than that: config-5 share (420 slots+12*rows per partition) 3.30 -> 2.70 ms, config 2
+    (49 per partition) 0.271 -> 0.354 ms.  PNA_B200_DYNAMIC_TAIL=0/1 overrides."""
+    env = os.environ.get("PNA_B200_DYNAMIC_TAIL")
+    if env is not None:
+        return env != "0"
+    return csr.n_part > 0 and (csr.n_edges + 12 * csr.n_nodes) / csr.n_part >= DYNAMIC_TAIL_MIN_PARTITION_COST
+
+
 def _check_scaler_degree(t: torch.Tensor, n_rows: int, dev) -> torch.Tensor:
     if t.dtype != torch.int32 or t.device != dev or t.numel() != n_rows or not t.is_contiguous():
         raise ValueError("scaler_degree must be a contiguous int32 [n_rows] tensor on the same device")
@@ -130,6 +144,8 @@ def aggregate_forward(gathered: torch.Tensor, csr: CSRGraph, aggregators: Names,
         row_ids=_ptr(row_ids), n_row_ids=0 if row_ids is None else int(row_ids.numel()))
     if scaler_degree is not None:
         d.scaler_degree = _check_scaler_degree(scaler_degree, N, dev).data_ptr()
+    if view is None and row_ids is None and _dynamic_tail(csr):
+        d.work_counter = _ptr(csr.work_counter())      # the whole graph in one launch: dynamic tail of the streamed kernel
     if view is None and row_ids is None:
         view = csr.full_view()
         if fold_finalize_enabled() and not skip_hubs and peer is None:

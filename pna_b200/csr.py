@@ -95,6 +95,15 @@ class CSRGraph:
             self._partials["done"] = buf
         return buf
 
+    def work_counter(self) -> torch.Tensor:
+        """One int32 of scratch for the dynamic tail of the streamed kernel (pna_agg_t.work_counter); zeroed by the library
+        before every launch.  One per CSR: calls that share a CSR must be stream-ordered (as for hub_partials)."""
+        buf = self._partials.get("work")
+        if buf is None:
+            buf = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._partials["work"] = buf
+        return buf
+
     def masked_view(self, row_mask: torch.Tensor) -> LightView:
         """Light view of the rows with ``row_mask != 0`` only (uint8/bool [N]); other rows are skipped by the kernel."""
         N, dev = self.n_nodes, self.device

@@ -36,6 +36,8 @@ struct KParams {
   const int* row_ids; long long n_row_ids;
   const int* lrowptr; const int* ldeg; const int* lcol; const int* part; int n_part;   // light view (nullable)
   long long n_view_rows;   // > n_rows: view rows n_rows + c are chunk pseudo-rows reduced into partials[c]
+  int* work_ctr;           // nullable: counter through which the last partitions are handed out dynamically
+  int n_static;            // partitions [0, n_static) are dealt out statically (set by the launcher)
   int hub_merged;          // 1: every split row's total already sits in its first partial slot (k_hub_tree ran)
   const int* sdeg;         // nullable [n_rows]: degree seen by the scalers (default: the in-degree of the row)
   int n_fpass;             // > 1: the streamed kernel makes this many passes over its rows, one feature block each

@@ -10,6 +10,7 @@ static int launch_fsplit(const KParams& p_in, cudaStream_t st) {
   constexpr int VEC = 2, K = 1, DEPTH = 1;
   KParams p = p_in;
   p.n_fpass = (p.F + 32 * VEC * K - 1) / (32 * VEC * K);
+  p.work_ctr = nullptr;       // static assignment only on this experimental path
   constexpr size_t smem = StreamGeom<float, VEC, K, DEPTH>::kSmem;
   auto kern = k_rows_stream<float, VEC, K, Cfg, false, DEPTH, false>;
   static int resident = 0;

@@ -480,15 +480,6 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   const int warp = threadIdx.x >> 5;
   fill_scale_lut(s_scale_lut, p, threadIdx.x, kStreamThreads);
 
-  // this warp's rows: a contiguous range of the light view, cut at equal-cost partition boundaries
-  const long long W = (long long)gridDim.x * (kStreamThreads / 32);
-  const long long w = (long long)blockIdx.x * (kStreamThreads / 32) + warp;
-  const int pa = __ldg(p.part + (int)((w * p.n_part) / W));
-  const int pb = __ldg(p.part + (int)(((w + 1) * p.n_part) / W));
-  if (pa >= pb) return;   // warp-uniform; no CTA-wide barrier is used below
-  const int Q0 = __ldg(p.lrowptr + pa);
-  const int Te = __ldg(p.lrowptr + pb) - Q0;      // length of this warp's slot stream
-
   // shared memory: [warps][2] mbarriers, then per warp a ring of 2*H slots
   const unsigned smem0 = smem_u32(smem);
   const unsigned bar0 = smem0 + warp * 16;
@@ -505,6 +496,21 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
   (void)bar0;
 #endif
 
+  // this warp's rows: first a contiguous range of the light view cut at equal-cost partition boundaries -- the first
+  // n_static partitions are dealt out statically, one contiguous range per warp (one uninterrupted slot stream).  The
+  // remaining partitions are handed out one at a time through an atomic counter: the static ranges finish at different
+  // times (17 % of the SM cycles were idle at the tail of configs 2 and 5), the dynamic ones fill the gap.
+  const long long W = (long long)gridDim.x * (kStreamThreads / 32);
+  const long long w = (long long)blockIdx.x * (kStreamThreads / 32) + warp;
+  const int n_static = p.work_ctr ? p.n_static : p.n_part;
+  int pi_a = (int)((w * n_static) / W), pi_b = (int)(((w + 1) * n_static) / W);
+#pragma unroll 1
+ for (;;) {
+  const int pa = __ldg(p.part + pi_a);
+  const int pb = __ldg(p.part + pi_b);
+  const int Q0 = __ldg(p.lrowptr + pa);
+  const int Te = __ldg(p.lrowptr + pb) - Q0;      // length of this slot stream
+  if (pa < pb) {                                  // warp-uniform; no CTA-wide barrier is used below
   const int* __restrict__ lcol = p.lcol + Q0;
   // feature passes: with n_fpass > 1 every warp walks its rows n_fpass times, each time over a block of G*VEC*K
   // features -- the gathered working set of a pass is n_src * (block bytes), sized to stay L2-resident
@@ -691,9 +697,18 @@ __global__ void __launch_bounds__(kStreamThreads, tiled_min_blocks(VEC, K)) k_ro
     dg = dgN; rid = ridN;
   }
 #if !PNA_STREAM_TMA
-  if (n_fpass > 1) { cp_async_wait<0>(); __syncwarp(); }
+  if (n_fpass > 1 || p.work_ctr) { cp_async_wait<0>(); __syncwarp(); }    // the ring is refilled from its first segment
 #endif
  }  // feature passes
+  }  // pa < pb
+  if (!p.work_ctr) break;
+  int g = 0;
+  if (lane == 0) g = atomicAdd(p.work_ctr, 1);
+  g = __shfl_sync(FULL, g, 0);
+  pi_a = n_static + g;
+  if (pi_a >= p.n_part) break;
+  pi_b = pi_a + 1;
+ }  // ranges
 }
 
 // ---- hubs, pass 1: one lane group per chunk of `chunk` slots -> fp32 partials ------------------------------
@@ -950,6 +965,12 @@ static int launch_config(const KParams& p_in, cudaStream_t st) {
     long long gxs = (slots + 8 * (kStreamThreads / 32) - 1) / (8 * (kStreamThreads / 32)); /* >= 8 rows per warp */ \
     if (gxs > resident) gxs = resident;                                                                            \
     if (gxs < 1) gxs = 1;                                                                                          \
+    if (p.work_ctr) {   /* dynamic tail: the last ~30 % of the partitions, if every warp still gets static work */  \
+      const long long nw = gxs * (kStreamThreads / 32);                                                            \
+      p.n_static = (int)((long long)p.n_part * 7 / 10);                                                            \
+      if (gy != 1 || p.n_static < nw || gxs < resident) p.work_ctr = nullptr;                                      \
+      else PNA_CUDA_TRY(cudaMemsetAsync(p.work_ctr, 0, sizeof(int), st));                                          \
+    }                                                                                                              \
     kern<<<dim3((unsigned)gxs, gy), kStreamThreads, smem, st>>>(p);                                                \
   } while (0)
         // single-GPU kernels exist with and without the folded finalize; the peer (DEPTH 2) kernels without
