@@ -268,7 +268,10 @@ def run_ours(args):
             raise SystemExit("launch N > 1 with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 or os.environ.get("PNA_BENCH_FORCE_MULTI") == "1":     # (the latter: exercise bench_multi.py on one GPU)
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29599")
+            os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
         dist.init_process_group("nccl", device_id=dev)
         import bench_multi
         return bench_multi.run(args)

@@ -79,8 +79,8 @@ def make_config4(rank, world, dev):
     n_local = per * 70
     ids = torch.arange(g0 * 70, g0 * 70 + n_local, device=dev)
     x = synth.hash_features(ids, 64)
-    return dict(name="config4", f=64, n_local=n_local, n_total=total_graphs * 70, src=ei[0], dst=ei[1], x=x, lo=g0 * 70,
-                bounds=None)
+    return dict(name="config4", f=64, n_local=n_local, n_total=total_graphs * 70, src=ei[0], dst=ei[1], dst_local=ei[1], x=x,
+                lo=g0 * 70, bounds=None)       # src / dst are rank-local node ids: no edge leaves the rank
 
 
 def make_config5(rank, world, dev):
@@ -105,7 +105,7 @@ def make_config5(rank, world, dev):
     del chunks
     src, dst = torch.cat(srcs), torch.cat(dsts)
     x = synth.hash_features(torch.arange(lo, hi, device=dev), f)
-    return dict(name="config5", f=f, n_local=hi - lo, n_total=n_total, src=src, dst=dst, x=x, lo=lo, bounds=bounds,
+    return dict(name="config5", f=f, n_local=hi - lo, n_total=n_total, src=src, dst=dst, dst_local=dst - lo, x=x, lo=lo, bounds=bounds,
                 local_deg=deg[lo:hi].clone(), max_in_degree=int(deg.max()))
 
 
@@ -132,7 +132,7 @@ def run(args):
     sync = lambda: dist.barrier(device_ids=[local])
 
     # degree histogram of the WHOLE graph -> avg_deg (the layer's ctor argument), identical on all ranks
-    local_deg = torch.bincount(w["dst"] - w["lo"], minlength=n_local)
+    local_deg = torch.bincount(w["dst_local"], minlength=n_local)
     hist = torch.bincount(local_deg)
     hlen = int(_allmax(hist.numel(), dev))
     hist_all = torch.zeros(hlen, dtype=torch.int64, device=dev)
@@ -163,6 +163,8 @@ def run(args):
         planes["pull"] = lambda: agg.aggregate(AGGRS, SCALERS, avg_deg, out=out)
 
         def col_to_global(idx):
+            if halo_ids_cpu.numel() == 0:
+                return idx + w["lo"]
             return torch.where(idx < n_local, idx + w["lo"], halo_ids_cpu[(idx - n_local).clamp(min=0)])
         if os.environ.get("PNA_BENCH_ALL_PLANES", "1") == "1":
             hplan = pdist.build_halo_plan(w["src"], w["dst"], bounds, rank, world)

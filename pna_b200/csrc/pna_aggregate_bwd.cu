@@ -49,7 +49,7 @@ struct Coef {
 
 template <typename T, int VEC>
 __device__ __forceinline__ void load_m(const KParams& p, int src, int f, const float (&bias)[VEC], bool has_bias, float (&m)[VEC]) {
-  Io<T, VEC>::load(gathered_row<T>(p, src) + f, m);
+  Io<T, VEC>::load(local_row<T>(p, src) + f, m);
   if (has_bias) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) m[i] = __fadd_rn(m[i], bias[i]);
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kBwdThreads) k_bwd_rows(const BParams b) {
 #pragma unroll
     for (int u = 0; u < UB; ++u) src[u] = (e + u < end) ? (p.col ? __ldg(p.col + e + u) : e + u) : -1;
 #pragma unroll
-    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(gathered_row<T>(p, src[u]) + lc.f);
+    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(local_row<T>(p, src[u]) + lc.f);
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
       if (src[u] >= 0) {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kBwdThreads) k_bwd_rows(const BParams b) {
 #pragma unroll
     for (int u = 0; u < UB; ++u) src[u] = (e + u < end) ? (p.col ? __ldg(p.col + e + u) : e + u) : -1;
 #pragma unroll
-    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(gathered_row<T>(p, src[u]) + lc.f);
+    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(local_row<T>(p, src[u]) + lc.f);
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
       if (src[u] >= 0) {
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kBwdThreads) k_bwd_hub_stats(const BParams b) 
 #pragma unroll
     for (int u = 0; u < UB; ++u) src[u] = (e + u < end) ? (p.col ? __ldg(p.col + e + u) : e + u) : -1;
 #pragma unroll
-    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(gathered_row<T>(p, src[u]) + lc.f);
+    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(local_row<T>(p, src[u]) + lc.f);
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
       if (src[u] >= 0) {
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kBwdThreads) k_bwd_hub_scatter(const BParams b
 #pragma unroll
     for (int u = 0; u < UB; ++u) src[u] = (e + u < end) ? (p.col ? __ldg(p.col + e + u) : e + u) : -1;
 #pragma unroll
-    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(gathered_row<T>(p, src[u]) + lc.f);
+    for (int u = 0; u < UB; ++u) if (src[u] >= 0) raw[u] = Io<T, VEC>::load_raw(local_row<T>(p, src[u]) + lc.f);
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
       if (src[u] >= 0) {
@@ -421,6 +421,7 @@ extern "C" int pna_aggregate_bwd(const pna_agg_t* d, const void* grad_out, int64
   if (d->n_rows == 0) return PNA_OK;
   PNA_REQUIRE(d->gathered && d->rowptr && grad_out && grad_gathered, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: null pointer");
   PNA_REQUIRE(d->peer_gathered == nullptr, PNA_ERR_UNSUPPORTED, "pna_aggregate_bwd: peer-memory graphs are forward-only");
+  PNA_REQUIRE(d->ld_gathered < 0x3fffffffll, PNA_ERR_UNSUPPORTED, "pna_aggregate_bwd: row pitch too large");
   PNA_REQUIRE(d->split_threshold >= 2, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: bad split threshold");
   if (d->n_hubs > 0)
     PNA_REQUIRE(d->hub_info && d->chunk_items && d->hub_partials && d->chunk_edges >= 1, PNA_ERR_BAD_ARG,

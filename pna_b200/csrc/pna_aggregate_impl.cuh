@@ -911,6 +911,18 @@ static inline int feat_split_mode() {
   return mode;
 }
 
+// tuning knob (experiments only): PNA_B200_OVERSUB = CTAs launched per resident CTA slot of the streamed kernel (default 1:
+// a persistent grid).  > 1: more, shorter static ranges; the hardware hands the extra CTAs to the SMs that finish first.
+static inline int stream_oversubscription() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("PNA_B200_OVERSUB");
+    v = e ? atoi(e) : 1;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
+
 template <typename T, int VEC, int G, int K, int U>
 static int launch_config(const KParams& p_in, cudaStream_t st) {
   constexpr int RPW = 32 / G;
@@ -963,7 +975,7 @@ static int launch_config(const KParams& p_in, cudaStream_t st) {
       resident = (nb > 0 ? nb : 1) * sms;                                                                          \
     }                                                                                                              \
     long long gxs = (slots + 8 * (kStreamThreads / 32) - 1) / (8 * (kStreamThreads / 32)); /* >= 8 rows per warp */ \
-    if (gxs > resident) gxs = resident;                                                                            \
+    if (gxs > (long long)resident * stream_oversubscription()) gxs = (long long)resident * stream_oversubscription(); \
     if (gxs < 1) gxs = 1;                                                                                          \
     if (p.work_ctr) {   /* dynamic tail: the last ~30 % of the partitions, if every warp still gets static work */  \
       const long long nw = gxs * (kStreamThreads / 32);                                                            \
