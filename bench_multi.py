@@ -340,6 +340,7 @@ def _e2e(args, w, world, rank, dev, local, avg_deg, hist, e_total, sync):
     d2h = _allsum(outh.numel() * 4, dev)
     return {"value": e_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "pinned": True,
-            "what": "per rank, every step: H2D of its feature rows and in-edge list (pinned), CSR + pull-plan build, flag barrier + "
-                    "halo pull, aggregation (compact [N,4F]) + post-MLP linear on the tensor cores in row blocks overlapped with the "
+            "what": "per rank, every step: H2D of its feature rows and in-edge list (pinned), CSR" +
+                    (" build" if w["bounds"] is None else " + pull-plan build, flag barrier + halo pull") +
+                    ", aggregation (compact [N,4F]) + post-MLP linear on the tensor cores in row blocks overlapped with the "
                     "D2H of its output rows; max over ranks of the wall time"}

@@ -10,7 +10,7 @@ from .csr import CSRGraph, build_csr, clear_csr_cache, csr_from_edge_index
 from .pyg import PNAConv, PNAConvSimple
 from .graph import Graph, avg_d_from_graphs, graph_csr
 from .dgl_layers import PNALayer, PNASimpleLayer
-from . import dense, readout
+from . import dense, padding, readout
 
 __all__ = ["PnaError", "build_library", "aggregate_forward", "avg_deg_from_histogram", "pna_aggregate", "CSRGraph",
            "build_csr", "clear_csr_cache", "csr_from_edge_index", "PNAConv", "PNAConvSimple", "Graph", "avg_d_from_graphs",

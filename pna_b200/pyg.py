@@ -15,7 +15,7 @@ from torch.nn import Linear, Module, ModuleList, ReLU, Sequential
 
 from . import padding as pad
 from .aggregate import avg_deg_from_histogram, pna_aggregate, row_scales
-from .linear import compact_path_ok, post_linear, post_linear_scaled
+from .linear import compact_path_ok, linear_tf32x3, post_linear, post_linear_scaled
 from .csr import CSRGraph, csr_from_edge_index, tensor_version
 
 _AGGRS = ("sum", "mean", "min", "max", "var", "std")          # aggregators.py:35-42
@@ -265,6 +265,68 @@ class PNAConv(Module):
         hs = [nn(h[:, t]) for t, nn in enumerate(self.pre_nns)]
         return torch.cat(hs, dim=1)
 
+    # -- inference on the tensor cores: every GEMM of the layer through pna_linear_fwd (3xTF32, fp32-accurate) --------------
+    def _tensor_core_pack(self, Fp: int):
+        """Weights of the three dense steps at the shapes pna_linear_fwd takes (K a multiple of 32, 64/128/256 outputs), zero
+        padded; cached per parameter version like `_prepared`:
+          U|V      [N, in -> K1] x [O1, K1]:  O1 >= 2*T*Fp rows (U block, V block, zero rows), bias only on the V block;
+          towers   [N, T*W -> K2] x [O2, K2]: BLOCK-DIAGONAL -- output columns t*F_out.. read only tower t's W input
+                   columns, so one launch does the first post Linear of every tower (pna.py:132) and its output is already
+                   the concatenation torch.cat(outs, dim=1) of pna.py:134;
+          lin      [N, O2] x [O3, O2]:        the final Linear (pna.py:135) on that buffer; pad columns meet zero weights."""
+        params = [p_ for nn in list(self.pre_nns) + list(self.post_nns) for p_ in nn[0].parameters()] + list(self.lin.parameters())
+        key = ("tc", Fp, tuple(tensor_version(p_) for p_ in params), tuple(p_.data_ptr() for p_ in params))
+        if getattr(self, "_tc", None) is not None and self._tc[0] == key:
+            return self._tc[1]
+        up32 = lambda v: (v + 31) // 32 * 32
+        pick = lambda v: 64 if v <= 64 else 128 if v <= 128 else 256
+        T, Fo = self.towers, self.F_out
+        w_uv, b_uv, w_post, b_post = self._prepared(Fp)
+        dev, dt = w_uv.device, w_uv.dtype
+        K1, O1 = up32(w_uv.size(1)), pick(w_uv.size(0))
+        w1 = torch.zeros((O1, K1), dtype=dt, device=dev); w1[: w_uv.size(0), : w_uv.size(1)] = w_uv
+        b1 = torch.zeros(O1, dtype=dt, device=dev); b1[: b_uv.numel()] = b_uv
+        W = w_post.size(2)                                          # (1 + S*A) * Fp columns per tower
+        K2, O2 = up32(T * W), pick(T * Fo)
+        w2 = torch.zeros((O2, K2), dtype=dt, device=dev)
+        b2 = torch.zeros(O2, dtype=dt, device=dev)
+        for t in range(T):
+            w2[t * Fo:(t + 1) * Fo, t * W:(t + 1) * W] = w_post[t]
+            b2[t * Fo:(t + 1) * Fo] = b_post[t]
+        O3 = pick(self.out_channels)
+        w3 = torch.zeros((O3, O2), dtype=dt, device=dev); w3[: self.out_channels, : T * Fo] = self.lin.weight
+        b3 = torch.zeros(O3, dtype=dt, device=dev); b3[: self.out_channels] = self.lin.bias
+        pack = dict(K1=K1, w1=w1, b1=b1, K2=K2, w2=w2, b2=b2, w3=w3, b3=b3)
+        self._tc = (key, pack)
+        return pack
+
+    def _tensor_core_ok(self, x: Tensor, edge_attr, Fp: int) -> bool:
+        import os
+        T = self.towers
+        return (x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and edge_attr is None and self.pre_layers == 1
+                and self.edge_dim is None and len(self.post_nns[0]) == 1 and 2 * T * Fp <= 256 and T * self.F_out <= 256
+                and self.out_channels <= 256 and x.size(0) > 0 and os.environ.get("PNA_B200_TENSOR_LINEAR", "1") != "0")
+
+    def _forward_tensor_cores(self, x: Tensor, csr: CSRGraph, x_self: Tensor, Fp: int) -> Tensor:
+        """No-grad forward with every dense step on the tensor cores (ZINC-shaped PNAConv(75,75,T=5): 1.73 -> see DESIGN.md);
+        same arithmetic as the generic path up to fp32 summation order."""
+        from .aggregate import aggregate_forward, output_width
+        tc = self._tensor_core_pack(Fp)
+        T, N = self.towers, x.size(0)
+        uv = linear_tf32x3(pad.pad_cols(x, tc["K1"]), tc["w1"], tc["b1"])                       # [N, O1]: U | V | 0
+        U, V = uv[:, : T * Fp], uv[:, T * Fp: 2 * T * Fp]
+        # aggregation writes into a [N, K2] buffer whose pad columns are zero (allocated once per N: the kernel never
+        # touches them), so the block-diagonal GEMM may read K2 columns
+        width = T * output_width(Fp, len(self.aggregators), len(self.scalers), True)
+        buf = getattr(self, "_tc_buf", None)
+        if buf is None or buf.size(0) != N or buf.size(1) != tc["K2"] or buf.device != x.device:
+            buf = torch.zeros((N, tc["K2"]), dtype=torch.float32, device=x.device)
+            self._tc_buf = buf
+        aggregate_forward(V, csr, self.aggregators, self.scalers, self.avg_deg, towers=T, row_bias=U, self_feat=x_self,
+                          self_divided=self.divide_input, out=buf[:, :width] if width < tc["K2"] else buf)
+        h = linear_tf32x3(buf, tc["w2"], tc["b2"])                                               # [N, O2] = cat over towers | 0
+        return linear_tf32x3(h, tc["w3"], tc["b3"])[:, : self.out_channels]
+
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Optional[Tensor] = None, *,
                 deg: Optional[Tensor] = None, csr: Optional[CSRGraph] = None) -> Tensor:
         csr = _resolve_csr(x, edge_index, csr)
@@ -277,6 +339,8 @@ class PNAConv(Module):
             x_self = pad.pad_blocks(x, T, Fi, Fp)
         else:
             x_self = pad.pad_cols(x, Fp)
+        if self._tensor_core_ok(x, edge_attr, Fp):
+            return self._forward_tensor_cores(x, csr, x_self, Fp)
         common = dict(towers=T, self_feat=x_self, self_divided=self.divide_input)
         if edge_attr is None and self.pre_layers == 1 and self.edge_dim is None:
             U, V = self._affine_terms(x, Fp)

@@ -924,3 +924,33 @@ def test_layer_output_error_at_config2_width(P, O, arxiv):
     assert err_gpu <= 1e-5, err_gpu
     assert err_gpu <= 2.0 * err_ref + 1e-7, (err_gpu, err_ref)
     assert (got - want32).abs().max().item() <= 5e-5
+
+
+# ---- full PNAConv, inference: every dense step on the tensor cores (3xTF32) vs the reference's op sequence -----------------
+@pytest.mark.parametrize("cin,cout,towers,divide", [(75, 75, 5, True), (16, 16, 4, True), (15, 20, 5, False), (32, 32, 1, False)])
+def test_conv_tensor_core_inference_path_matches_reference(P, O, cin, cout, towers, divide, monkeypatch):
+    """U|V pre-GEMM, block-diagonal tower post-GEMM and the final Linear through pna_linear_fwd (zero-padded to the kernel's
+    shapes) against the CPU oracle, and against the same layer with the tensor-core path switched off (library GEMMs)."""
+    n, e = 5000, 30000
+    ei = rand_graph(n, e, seed=cin + towers)
+    x = torch.randn(n, cin, generator=torch.Generator().manual_seed(cout))
+    deg = torch.bincount(torch.bincount(ei[1], minlength=n))
+    ref = O.PNAConvOracle(cin, cout, A4, S3, deg, towers=towers, divide_input=divide)
+    lay = P.PNAConv(cin, cout, A4, S3, deg, towers=towers, divide_input=divide)
+    lay.load_state_dict(ref.state_dict())
+    lay = lay.to(dev())
+    with torch.no_grad():
+        want = ref(x, ei)
+        assert lay._tensor_core_ok(x.to(dev()), None, P.padding.padded_width(lay.F_in, torch.float32))
+        got = lay(x.to(dev()), ei.to(dev())).cpu()
+        monkeypatch.setenv("PNA_B200_TENSOR_LINEAR", "0")
+        got_lib = lay(x.to(dev()), ei.to(dev())).cpu()
+    assert got.shape == want.shape
+    torch.testing.assert_close(got, want, **LAYER_TOL)
+    torch.testing.assert_close(got_lib, want, **LAYER_TOL)
+    # parameters changed in place -> the packed weights are rebuilt
+    with torch.no_grad():
+        lay.lin.weight.mul_(2.0); lay.lin.bias.mul_(2.0)
+        monkeypatch.delenv("PNA_B200_TENSOR_LINEAR")
+        got2 = lay(x.to(dev()), ei.to(dev())).cpu()
+    torch.testing.assert_close(got2, 2.0 * want, rtol=2e-5, atol=2e-5)
