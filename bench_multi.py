@@ -217,6 +217,14 @@ def run(args):
         other[name] = {"ms_per_step": ms, "edges_per_s": e_total / (ms * 1e-3), "parity_ok": all(o[0] for o in ok2),
                        "parity_max_err": max(o[1] for o in ok2)}
 
+    # ---- the aggregation alone on every rank (no exchange, no barrier: the ranks are not coupled in this measurement)
+    agg_alone = None
+    if agg is not None:
+        ts = bc.timed_steps(lambda: aggregate_forward(agg.x_ext, agg.csr, AGGRS, SCALERS, avg_deg, out=out), 5, 2, flush, None)
+        alone = [None] * world
+        dist.all_gather_object(alone, sum(ts) / len(ts))
+        agg_alone = alone
+
     # ---- pull kernel alone (NVLink roofline of the exchange)
     nvlink = None
     if agg is not None and _allmax(halo_rows, dev) > 0:
@@ -250,7 +258,8 @@ def run(args):
             "partition": {"rows_per_rank": [b[1] for b in by_all], "edges_per_rank": [b[2] for b in by_all],
                           "remote_edge_fraction": sum(b[3] for b in by_all) / max(e_total, 1),
                           "halo_rows_per_rank": [b[4] for b in by_all], "split_rows_per_rank": [b[5] for b in by_all],
-                          "max_in_degree": max(b[6] for b in by_all), "ms_per_step_per_rank": all_ms, "gpu_numa_node": numa,
+                          "max_in_degree": max(b[6] for b in by_all), "ms_per_step_per_rank": all_ms,
+                          "aggregation_alone_ms_per_rank": agg_alone, "gpu_numa_node": numa,
                           "generation_s": gen_s},
             "parity": {"ok": all(p["ok"] for p in par_all), "parity_max_err": max(max(p["max_err_light"], p["max_err_split_vs_f64"]) for p in par_all),
                        "max_err_over_tolerance": max(p["max_err_over_tol"] for p in par_all),
