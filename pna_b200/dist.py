@@ -291,7 +291,14 @@ def _symmetric_tensor(shape, dtype, dev, rank: int, world: int, group):
 
 
 class PeerAggregator:
-    """Gather fused with the exchange: remote rows are read over NVLink inside the aggregation kernel."""
+    """Gather fused with the exchange: remote rows are read over NVLink inside the aggregation kernel.
+
+    Protocol: every rank writes its rows into ``x_local`` -> ``barrier()`` -> ``aggregate()``.  The barrier orders "all ranks
+    have written" before the gathers; NOTHING orders the end of the peers' gathers before this rank's next write into
+    ``x_local`` -- a rank that finishes ``aggregate()`` early must not overwrite its rows while slower peers may still be
+    reading them.  Either call ``barrier()`` again after ``aggregate()`` before rewriting ``x_local`` (what a multi-layer net
+    using ONE buffer has to do), or alternate between two aggregators / buffers per layer as ``PullAggregator`` does
+    (``flip()``), where the next layer's barrier separates this layer's reads from the writes two layers later."""
 
     def __init__(self, src_global: torch.Tensor, dst_global: torch.Tensor, bounds: torch.Tensor, rank: int, world: int,
                  n_feat: int, dtype=torch.float32, group=None):

@@ -116,3 +116,38 @@ def test_cache_keys_accept_inference_mode_tensors():
     v0 = tensor_version(u)
     u.add_(1)
     assert tensor_version(u) == v0 + 1
+
+
+@pytest.mark.parametrize("cin,cout,towers,divide", [(75, 75, 5, True), (15, 20, 5, False), (16, 16, 4, True), (32, 32, 1, False)])
+def test_conv_tensor_core_weight_pack_is_the_reference_algebra(cin, cout, towers, divide):
+    """PNAConv._tensor_core_pack (pna_b200/pyg.py): the zero-padded U|V weight, the BLOCK-DIAGONAL tower weight and the padded
+    final Linear reproduce pna.py:131-135 when applied with plain matmuls on CPU (the GPU test runs them through
+    pna_linear_fwd)."""
+    import torch.nn.functional as Fn
+    from pna_b200 import PNAConv, padding as pad
+    torch.manual_seed(cin + towers)
+    lay = PNAConv(cin, cout, ["mean", "max", "min", "std"], ["identity", "amplification", "attenuation"], torch.tensor([0, 4, 3, 1]),
+                  towers=towers, divide_input=divide)
+    T, Fi, Fo = towers, lay.F_in, lay.F_out
+    Fp = pad.padded_width(Fi, torch.float32)
+    with torch.no_grad():
+        tc = lay._tensor_core_pack(Fp)
+        x = torch.randn(23, cin)
+        uv = pad.pad_cols(x, tc["K1"]) @ tc["w1"].t() + tc["b1"]
+        U, V = lay._affine_terms(x, Fp)
+        torch.testing.assert_close(uv[:, : T * Fp], U, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(uv[:, T * Fp: 2 * T * Fp], V, rtol=1e-6, atol=1e-6)
+        assert uv[:, 2 * T * Fp:].abs().sum() == 0
+        W = 13 * Fp
+        out = torch.randn(23, T, W)                                   # stands for cat([x_t, aggregate_t]) at the padded width
+        buf = torch.zeros(23, tc["K2"]); buf[:, : T * W] = out.reshape(23, T * W)
+        h = buf @ tc["w2"].t() + tc["b2"]
+        want_h = torch.cat([Fn.linear(out[:, t], pad.expand_weight_cols(nn[0].weight, 13, Fi, Fp), nn[0].bias)
+                            for t, nn in enumerate(lay.post_nns)], 1)
+        torch.testing.assert_close(h[:, : T * Fo], want_h, rtol=1e-5, atol=1e-5)
+        assert h[:, T * Fo:].abs().sum() == 0
+        y = (h @ tc["w3"].t() + tc["b3"])[:, :cout]
+        torch.testing.assert_close(y, lay.lin(want_h), rtol=1e-5, atol=1e-5)
+        # in-place parameter update -> new pack
+        lay.lin.bias.add_(1.0)
+        assert lay._tensor_core_pack(Fp) is not tc
