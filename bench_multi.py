@@ -49,7 +49,7 @@ def config_dict(world: int) -> dict:
     n_total = int(os.environ.get("PNA_BENCH_C5_NODES_PER_GPU", "1250000")) * world
     e_total = int(os.environ.get("PNA_BENCH_C5_EDGES_PER_GPU", "12500000")) * world
     f = int(os.environ.get("PNA_BENCH_C5_FEAT", "256"))
-    row_cost = int(os.environ.get("PNA_BENCH_ROW_COST", "32"))
+    row_cost = int(os.environ.get("PNA_BENCH_ROW_COST", "72"))
     return {"workload": f"BASELINE.json configs[4]: power-law graph (Zipf 1.5 sources and destinations over random permutations), "
                         f"{n_total} nodes / {e_total} edges, F={f} fp32, contiguous destination ranges of equal cost (in-edges + "
                         f"{row_cost} per row) over {world} GPUs" + ("" if world == 8 else f" ({world}/8 scale)"),
@@ -90,7 +90,7 @@ def make_config5(rank, world, dev):
     n_total = int(os.environ.get("PNA_BENCH_C5_NODES_PER_GPU", "1250000")) * world
     e_total = int(os.environ.get("PNA_BENCH_C5_EDGES_PER_GPU", "12500000")) * world
     f = int(os.environ.get("PNA_BENCH_C5_FEAT", "256"))
-    row_cost = int(os.environ.get("PNA_BENCH_ROW_COST", "32"))
+    row_cost = int(os.environ.get("PNA_BENCH_ROW_COST", "72"))
     deg = torch.zeros(n_total, dtype=torch.int64, device=dev)
     chunks = []
     for s, d in synth.powerlaw_stream(n_total, e_total, dev, seed=0):
