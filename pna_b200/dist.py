@@ -1,28 +1,28 @@
-"""Destination-partitioned multi-GPU PNA aggregation (BASELINE.json configs 4/5).
+"""Destination-partitioned multi-GPU PNA aggregation (BASELINE.json configs[4]).
 
 The reference has no distributed code at all ("NCCL / collective call sites: None").  Rows
 (destinations) are independent, so the graph is cut into contiguous destination ranges, one per GPU / process.  A rank
 owns the features and the output rows of its range and all in-edges of its rows; sources may live on other ranks.
-Two ways to reach remote source rows, both behind ``pna_aggregate_fwd``:
+Three ways to reach remote source rows, all behind ``pna_aggregate_fwd``:
 
-* ``peer`` (default on NVLink boxes): every rank's feature buffer is mapped into every process (symmetric memory /
-  CUDA IPC over NVLink 5).  ``col`` encodes ``owner << shift | row`` and the aggregation kernel gathers remote rows
-  straight from the owner's HBM with the same asynchronous copies it uses for local rows -- gather and exchange are
-  ONE kernel, transfer overlapped with the reduction by the kernel's own ring of in-flight copies; no pack, no halo
-  buffer, no unpack.
-* ``halo`` (the north-star's wording; also the baseline the peer path is measured against): unique remote sources are
-  exchanged once per graph; per layer the owners pack the requested rows (``pna_gather_rows``) and ONE NCCL
-  all-to-all-v (``torch.distributed.all_to_all_single``) lands them behind the local rows, ``[local ; halo]``; rows
-  whose sources are all local are reduced while the all-to-all is in flight (masked light views), the rest afterwards.
+* ``pull`` (``PullAggregator``, what ``bench.py --gpus N`` times): the rank's DE-DUPLICATED remote sources are listed once
+  per graph, locally (the puller names the rows; no id exchange); per layer a device-side flag barrier
+  (``pna_peer_barrier``) and ONE kernel of NVLink peer loads (``pna_halo_pull``) fill the halo tail of the rank's
+  ``[local ; halo]`` buffer, and the aggregation gathers from local HBM only.  A remote row crosses NVLink once per layer
+  however often it is gathered -- what a power-law graph needs.
+* ``halo`` (``HaloAggregator``; the north star's wording, measured beside pull): the same rows through a pack kernel
+  (``pna_gather_rows``) and ONE NCCL all-to-all-v (``torch.distributed.all_to_all_single``); rows whose sources are all
+  local can be reduced while the all-to-all is in flight (masked light views).
+* ``peer`` (``PeerAggregator``): ``col`` encodes ``owner << shift | row`` and the aggregation kernel gathers remote rows
+  straight from the owner's HBM with the same asynchronous copies it uses for local rows -- gather and exchange are ONE
+  kernel, no halo buffer at all; every remote EDGE crosses the link (peer lines are not cached in the local L2), so it
+  fits graphs whose remote rows are rarely reused.
 
 Host-side planning below is plain torch and runs on CPU tensors too (gloo), which is how tests/test_dist_cpu.py covers
 it without GPUs.
 """
 from __future__ import annotations
 
-import json
-import os
-import time
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -352,7 +352,7 @@ def _symmetric_rows(rows: int, n_feat: int, dtype, dev, rank: int, world: int, g
         return t, ptrs, {"opened": opened, "tensor": t, "how": f"CUDA IPC (symmetric memory unavailable: {exc})"}
 
 
-# ---- synthetic weak-scaling workload + bench ---------------------------------------------------------------------
+# ---- synthetic destination-partitioned workload (tools/dist_check.py; the bench lines come from bench_multi.py) ------
 def rank_graph(rank: int, world: int, n_local: int, e_local: int, n_feat: int, p_remote: float, seed: int = 0,
                skew: float = 3.0, dtype=torch.float32):
     """In-edges of rank's rows in a graph of world * n_local nodes: destinations skewed like synth.arxiv_like inside
@@ -367,135 +367,3 @@ def rank_graph(rank: int, world: int, n_local: int, e_local: int, n_feat: int, p
     src = torch.where(torch.rand(e_local, generator=g) < p_remote, any_src, local_src)
     x = torch.randn(n_local, n_feat, generator=g).to(dtype)
     return src, dst, x
-
-
-def bench_multi_gpu(args, metric, unit, aggrs, scalers, measured_peaks, ClockSampler):
-    """bench.py --gpus N (N > 1): weak scaling of config 2 -- every rank owns an ogbn-arxiv-sized destination range."""
-    from . import synth
-    from .aggregate import avg_deg_from_histogram
-    rank, world = dist.get_rank(), dist.get_world_size()
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dev = torch.device("cuda", local)
-    n_local, e_local, f = synth.ARXIV_NODES, synth.ARXIV_EDGES, 128
-    p_remote = float(os.environ.get("PNA_BENCH_P_REMOTE", "0.25"))
-    mode = os.environ.get("PNA_BENCH_DIST", "peer")
-    src, dst, x = rank_graph(rank, world, n_local, e_local, f, p_remote)
-    bounds = torch.arange(world + 1, dtype=torch.int64) * n_local
-    deg_hist = synth.degree_histogram(dst - rank * n_local, n_local)
-    avg_deg = avg_deg_from_histogram(deg_hist)
-    out = torch.empty((n_local, 12 * f), dtype=torch.float32, device=dev)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    flush_rd = torch.zeros(128 << 20, dtype=torch.float32, device=dev)
-
-    def l2_flush():
-        """write 512 MiB then read 512 MiB: previous data evicted, L2 left with clean lines (no write-back in the timed step)"""
-        flush.zero_()
-        flush_rd.sum()
-
-    if mode == "peer":
-        agg = PeerAggregator(src.to(dev), dst.to(dev), bounds, rank, world, f)
-        agg.x_local.copy_(x.to(dev))
-
-        def step():
-            agg.barrier()
-            agg.aggregate(aggrs, scalers, avg_deg, out=out)
-    else:
-        plan = build_halo_plan(src.to(dev), dst.to(dev), bounds, rank, world)
-        agg = HaloAggregator(plan, f, overlap=(mode != "halo_serial"))
-        agg.x_local.copy_(x.to(dev))
-
-        def step():
-            agg.aggregate(aggrs, scalers, avg_deg, out=out)
-
-    def timed(k, warm):
-        for _ in range(warm):
-            l2_flush(); step()
-        starts = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
-        ends = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
-        torch.cuda.synchronize(); dist.barrier(device_ids=[local]); torch.cuda.synchronize()
-        for i in range(k):
-            l2_flush()
-            starts[i].record(); step(); ends[i].record()
-        torch.cuda.synchronize(); dist.barrier(device_ids=[local]); torch.cuda.synchronize()
-        return [s.elapsed_time(e) for s, e in zip(starts, ends)]
-
-    with ClockSampler(local) as clk:
-        time.sleep(0.06)
-        for _ in range(300):          # ~0.15 s of the same kernels so the 20 Hz sampler sees the GPU under this load
-            step()
-        torch.cuda.synchronize()
-        per_step = timed(args.steps, args.warmup)
-        for _ in range(300):
-            step()
-        torch.cuda.synchronize()
-    # e2e at N GPUs: the layer call with this rank's features in pinned host memory -- H2D of x into the symmetric /
-    # halo buffer, the fused gather+exchange aggregation, post-MLP, D2H of the rank's output rows; graph plan cached
-    from .pyg import PNAConvSimple
-    torch.manual_seed(0)
-    lay = PNAConvSimple(f, f, aggrs, scalers, deg_hist).to(dev)
-    xh = x.pin_memory()
-    outh = torch.empty((n_local, f), dtype=torch.float32).pin_memory()
-
-    s_out = torch.cuda.Stream(device=dev)
-
-    def e2e_step():
-        agg.x_local.copy_(xh, non_blocking=True)
-        if mode == "peer":
-            agg.barrier()
-        a = agg.aggregate(aggrs, scalers, avg_deg, out=out)
-        main = torch.cuda.current_stream(dev)
-        blk = (n_local + 7) // 8
-        with torch.no_grad():
-            for r0 in range(0, n_local, blk):      # post-MLP in row blocks, each copied back while the next is computed
-                y = lay._post(a[r0:r0 + blk], None, a.dtype)         # first Linear on the tensor cores (pna_linear_fwd)
-                s_out.wait_stream(main)
-                with torch.cuda.stream(s_out):
-                    outh[r0:r0 + blk].copy_(y, non_blocking=True)
-                y.record_stream(s_out)
-        main.wait_stream(s_out)
-
-    k2 = max(3, min(args.steps, 20))
-    for _ in range(3):
-        e2e_step()
-    torch.cuda.synchronize(); dist.barrier(device_ids=[local]); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(k2):
-        e2e_step()
-    torch.cuda.synchronize(); dist.barrier(device_ids=[local])
-    e2e_ms = torch.tensor([1e3 * (time.perf_counter() - t0) / k2], dtype=torch.float64, device=dev)
-    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e = {"value": e_local * world / (float(e2e_ms) * 1e-3), "unit": unit, "ms_per_step": float(e2e_ms),
-           "h2d_bytes_per_step": n_local * f * 4 * world, "d2h_bytes_per_step": n_local * f * 4 * world,
-           "what": "per rank: H2D x (pinned) -> aggregation with remote sources -> post-MLP -> D2H; graph plan cached"}
-
-    total_ms = torch.tensor([sum(per_step)], dtype=torch.float64, device=dev)
-    dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    t_ms = float(total_ms) / args.steps
-    e_total = e_local * world
-    remote_edges = torch.tensor([int(((src < rank * n_local) | (src >= (rank + 1) * n_local)).sum())], dtype=torch.float64, device=dev)
-    dist.all_reduce(remote_edges)
-    if rank == 0:
-        by = synth.algorithmic_bytes(n_local, e_local, f, 4, 12 * f)
-        peak, peak_src = measured_peaks()
-        achieved = by["b_min"] / (t_ms * 1e-3) / 1e9
-        csr = agg.csr
-        n_launch = 1 + (2 if csr.n_hubs else 0)
-        if mode not in ("peer", "halo_serial"):
-            n_launch += 2      # pack kernel + second (boundary) aggregation launch
-        elif mode == "halo_serial":
-            n_launch += 1
-        line = {
-            "metric": metric, "value": e_total / (t_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{world} x ogbn-arxiv-shaped destination partitions (configs[1] per GPU)",
-                       "n_nodes": n_local * world, "n_edges": e_total, "n_feat": f, "aggregators": aggrs, "scalers": scalers,
-                       "remote_edge_fraction": float(remote_edges) / e_total, "remote_sources": mode,
-                       "parallelism": f"dst-partition x{world}", "l2": "flushed between timed steps (512 MiB written, then 512 MiB read so no dirty lines remain)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "note": "per-GPU B_min / max-over-ranks step time"},
-            "e2e": e2e, "gpu_launches": n_launch * args.steps, "clocks": clk.summary(), "cpu_baseline": None,
-        }
-        print(json.dumps(line))
-    dist.barrier(device_ids=[local])
-    dist.destroy_process_group()
