@@ -15,6 +15,7 @@ import torch.nn.functional as F
 from . import padding as pad
 from .aggregate import pna_aggregate, row_scales
 from .linear import compact_path_ok
+from .csr import tensor_version
 from .graph import graph_csr
 from .nn_blocks import FCLayer, MLP
 
@@ -94,19 +95,31 @@ class PNALayer(nn.Module):
 
     def _affine_terms(self, h, fp):
         """pretrans(cat[src h, dst h]) = W_s h_src + W_d h_dst + b (pna_layer.py:35-40): V = h W_s^T + b, U = h W_d^T,
-        each tower block padded to fp columns with zero weight rows."""
+        each tower block padded to fp columns with zero weight rows.  Both come out of ONE GEMM against the packed weight
+        [W_d ; W_s] (block-diagonal per tower with divide_input), which is rebuilt only when a parameter changed (without
+        autograd; with autograd it is part of the graph and rebuilt every call)."""
         it = self.input_tower
         lins = [tw.pretrans.fully_connected[0].linear for tw in self.towers]
-        Ws = [pad.expand_weight_rows(l.weight[:, :it], it, fp) for l in lins]
-        Wd = [pad.expand_weight_rows(l.weight[:, it:2 * it], it, fp) for l in lins]
-        b = torch.cat([F.pad(l.bias, (0, fp - it)) for l in lins])
-        if self.divide_input and len(lins) > 1:
-            V = torch.addmm(b, h, torch.block_diag(*Ws).t())
-            U = h @ torch.block_diag(*Wd).t()
+        params = [p_ for l in lins for p_ in (l.weight, l.bias)]
+        key = (fp, tuple(tensor_version(p_) for p_ in params), tuple(p_.data_ptr() for p_ in params))
+        cache = not (torch.is_grad_enabled() and any(p_.requires_grad for p_ in params))
+        hit = getattr(self, "_uv_pack", None)
+        if cache and hit is not None and hit[0] == key:
+            w_uv, b_uv = hit[1]
         else:
-            V = torch.addmm(b, h, torch.cat(Ws, 0).t())
-            U = h @ torch.cat(Wd, 0).t()
-        return U, V
+            Ws = [pad.expand_weight_rows(l.weight[:, :it], it, fp) for l in lins]
+            Wd = [pad.expand_weight_rows(l.weight[:, it:2 * it], it, fp) for l in lins]
+            b = torch.cat([F.pad(l.bias, (0, fp - it)) for l in lins])
+            if self.divide_input and len(lins) > 1:
+                w_uv = torch.cat([torch.block_diag(*Wd), torch.block_diag(*Ws)], 0)
+            else:
+                w_uv = torch.cat(Wd + Ws, 0)
+            b_uv = torch.cat([torch.zeros_like(b), b])
+            if cache:
+                self._uv_pack = (key, (w_uv, b_uv))
+        uv = torch.addmm(b_uv, h, w_uv.t())
+        half = uv.size(1) // 2
+        return uv[:, :half], uv[:, half:]
 
     def _edge_messages(self, csr, h, e):
         src, dst = csr.col.long(), csr.dst_of_slot
