@@ -337,6 +337,7 @@ def _e2e(args, w, world, rank, dev, local, avg_deg, hist, e_total, sync):
 
     k2 = max(2, min(args.steps, 5))
     with torch.no_grad():
+        torch.cuda.synchronize(); sync()      # pinning took a different time on every rank: enter the flag barrier together
         for _ in range(2):
             step()
         torch.cuda.synchronize(); sync(); torch.cuda.synchronize()
