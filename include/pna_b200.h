@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PNA_ABI_VERSION 7
+#define PNA_ABI_VERSION 8
 
 typedef void* pna_stream_t; /* a cudaStream_t / CUstream, passed opaquely */
 
@@ -239,6 +239,27 @@ int pna_aggregate_fwd(const pna_agg_t* desc, pna_stream_t stream);
  * the extremum (torch_scatter arg semantics). */
 int pna_aggregate_bwd(const pna_agg_t* desc, const void* grad_out, int64_t ld_grad_out, float* grad_gathered,
                       int64_t ld_grad_gathered, float* grad_row_bias, int64_t ld_grad_row_bias, pna_stream_t stream);
+
+/* The same gradient without one atomic per (edge, feature), for gathered rows (desc->col != NULL) -- three calls:
+ *  1. pna_aggregate_bwd_coef: per destination row i the gradient of a message is  c0_i + c1_i * m + routed min / max terms;
+ *     writes coef[i] = [c0_i + c1_i * row_bias[i]  (n_feat floats at column 0) | c1_i (n_feat floats at column c1_column)]
+ *     for every row with in-edges (other rows are left untouched and are never read in step 2), adds the min / max
+ *     gradients to grad_gathered[col[arg slot]] -- one scalar atomic per (row, feature); grad_gathered zero-initialised by
+ *     the caller as above -- and writes grad_row_bias (nullable).  c1_column >= n_feat, ld_coef >= c1_column + n_feat;
+ *     16-byte aligned choices (c1_column % 4 == 0, ld_coef % 4 == 0) get vector stores.  desc->hub_partials as for
+ *     pna_aggregate_bwd.
+ *  2. the caller sums the coefficient rows over the out-edges of every source row: pna_aggregate_fwd on the CSR of the
+ *     TRANSPOSED graph (pna_csr_build with source and destination swapped: n_nodes = n_src) with gathered = coef,
+ *     n_feat = ld_coef, one aggregator PNA_AGGR_SUM, one scaler PNA_SCALE_IDENTITY -> sums [n_src, ld_coef].
+ *  3. pna_aggregate_bwd_combine: grad_gathered[j, f] += sums[j, f] + gathered[j, f] * sums[j, c1_column + f].
+ * Same results up to fp32 summation order (reference: autograd of aggregators.py:9-32; tests/test_bwd_two_phase_math.py
+ * restates the algebra). */
+int pna_aggregate_bwd_coef(const pna_agg_t* desc, const void* grad_out, int64_t ld_grad_out, float* coef, int64_t ld_coef,
+                           int32_t c1_column, float* grad_gathered, int64_t ld_grad_gathered, float* grad_row_bias,
+                           int64_t ld_grad_row_bias, pna_stream_t stream);
+int pna_aggregate_bwd_combine(const float* coef_sums, int64_t ld_sums, int32_t c1_column, const void* gathered,
+                              int64_t ld_gathered, int32_t dtype, float* grad_gathered, int64_t ld_grad_gathered, int64_t n_src,
+                              int32_t n_feat, pna_stream_t stream);
 
 /* ---- halo rows for the destination-partitioned multi-GPU path (north_star: "single NCCL all-to-all for halo
  * source features per layer"): dst[i, :] = src[idx[i], :], n_feat elements per row.  Used to pack the send buffer. */

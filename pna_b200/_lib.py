@@ -27,7 +27,7 @@ BUILD_DIR = os.path.join(_HERE, "csrc", "build")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC"]
 
 # status codes / enums of include/pna_b200.h
-ABI_VERSION = 7
+ABI_VERSION = 8
 PNA_OK = 0
 PNA_F32, PNA_BF16 = 0, 1
 AGGR_CODES = {"sum": 0, "mean": 1, "min": 2, "max": 3, "var": 4, "std": 5, "_skip": 15}
@@ -38,6 +38,7 @@ FLAG_ZERO_ISOLATED, FLAG_SKIP_LIGHT, FLAG_SKIP_HUBS, FLAG_RELU_VAR, FLAG_GATHER_
 
 # every symbol the header declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = ("pna_csr_workspace_bytes", "pna_csr_build", "pna_csr_light_view", "pna_csr_light_view_workspace_bytes", "pna_aggregate_fwd", "pna_aggregate_bwd",
+                    "pna_aggregate_bwd_coef", "pna_aggregate_bwd_combine",
                     "pna_gather_rows", "pna_halo_pull", "pna_peer_barrier", "pna_linear_fwd", "pna_linear_scaled_fwd", "pna_row_scales", "pna_linear_workspace_bytes", "pna_query", "pna_last_error")
 
 
@@ -158,6 +159,12 @@ def lib() -> C.CDLL:
         L.pna_aggregate_bwd.restype = C.c_int
         L.pna_aggregate_bwd.argtypes = [C.POINTER(AggStruct), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                         C.c_int64, C.c_void_p]
+        L.pna_aggregate_bwd_coef.restype = C.c_int
+        L.pna_aggregate_bwd_coef.argtypes = [C.POINTER(AggStruct), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                             C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+        L.pna_aggregate_bwd_combine.restype = C.c_int
+        L.pna_aggregate_bwd_combine.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
+                                                C.c_int64, C.c_int32, C.c_void_p]
         L.pna_gather_rows.restype = C.c_int
         L.pna_gather_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_int32, C.c_void_p]

@@ -222,10 +222,35 @@ def aggregate_backward(grad_out: torch.Tensor, gathered: torch.Tensor, csr: CSRG
     if csr.n_hubs:   # per-chunk statistics + per-split-row coefficients
         scratch = torch.empty(((csr.n_chunks + csr.n_hubs) * 6, F), dtype=torch.float32, device=dev)
         d.hub_partials = scratch.data_ptr()
+    ld_go = grad_out.stride(0) if N > 1 else grad_out.size(1)
+    if messages_in_csr_order or csr.n_edges == 0 or csr.sources_unique or backward_mode() == "atomic" \
+            or 2 * _round_up(F, 4) > _lib.query(_lib.QUERY_MAX_FEATURES):
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().pna_aggregate_bwd(C.byref(d), grad_out.data_ptr(), ld_go, gg.data_ptr(), F, _ptr(gb), F,
+                                                    torch.cuda.current_stream(dev).cuda_stream))
+        return gg, gb
+    # shared source rows: coefficients per destination row -> their sums over the out-edges of every source row (the
+    # forward kernels on the transposed graph) -> grad_gathered; the only atomics route min / max (one per row and feature)
+    Fp = _round_up(F, 4)
+    coef = torch.empty((N, 2 * Fp), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().pna_aggregate_bwd(C.byref(d), grad_out.data_ptr(), grad_out.stride(0) if N > 1 else grad_out.size(1),
-                                                gg.data_ptr(), F, _ptr(gb), F, torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(_lib.lib().pna_aggregate_bwd_coef(C.byref(d), grad_out.data_ptr(), ld_go, coef.data_ptr(), 2 * Fp, Fp, gg.data_ptr(), F,
+                                                     _ptr(gb), F, torch.cuda.current_stream(dev).cuda_stream))
+    sums = aggregate_forward(coef, csr.transposed(gathered.size(0)), ["sum"], ["identity"], {"log": 1.0, "lin": 1.0})
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pna_aggregate_bwd_combine(sums.data_ptr(), sums.stride(0), Fp, _ptr(gathered),
+                                                        gathered.stride(0) if gathered.size(0) > 1 else F, _DTYPES[gathered.dtype],
+                                                        gg.data_ptr(), F, gathered.size(0), F, torch.cuda.current_stream(dev).cuda_stream))
     return gg, gb
+
+
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def backward_mode() -> str:
+    """PNA_B200_BWD=atomic keeps the one-call backward (a vector atomic per edge and feature chunk); default "coef"."""
+    return "atomic" if os.environ.get("PNA_B200_BWD", "coef") == "atomic" else "coef"
 
 
 class _PNAAggregate(torch.autograd.Function):

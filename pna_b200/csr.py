@@ -54,6 +54,7 @@ class CSRGraph:
     _deg: Optional[torch.Tensor] = field(default=None, repr=False)
     _dst: Optional[torch.Tensor] = field(default=None, repr=False)
     hot_source_fraction: float = 0.0      # pna_csr_t.hot_source_fraction: share of the gathers going to frequent sources
+    sources_unique: bool = False          # every source row has at most one out-edge (readouts): the backward's atomics never collide
 
     @property
     def device(self) -> torch.device:
@@ -103,6 +104,16 @@ class CSRGraph:
             buf = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._partials["work"] = buf
         return buf
+
+    def transposed(self, n_src: int) -> "CSRGraph":
+        """CSR of the reversed edges (rows = the ``n_src`` source rows, gathered from the destinations): what the backward
+        sums its per-destination coefficient rows over (pna_aggregate_bwd_coef).  Built on first use, kept with the graph."""
+        key = ("T", int(n_src))
+        t = self._partials.get(key)
+        if t is None:
+            t = build_csr(self.dst_of_slot, self.col.long(), int(n_src), n_src=self.n_nodes)
+            self._partials[key] = t
+        return t
 
     def masked_view(self, row_mask: torch.Tensor) -> LightView:
         """Light view of the rows with ``row_mask != 0`` only (uint8/bool [N]); other rows are skipped by the kernel."""

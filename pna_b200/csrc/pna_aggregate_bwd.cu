@@ -10,6 +10,14 @@
 // does; (C) evaluate grad_m per slot, accumulate it into grad_gathered[col[slot]] (vector atomics -- several
 // destinations share a source) and into grad_row_bias[row].  Rows at/above the split threshold are processed chunk by
 // chunk by three small kernels (statistics, coefficients, scatter), like the forward.
+//
+// pna_aggregate_bwd_coef (gathered rows, col != NULL): pass C and its one vector atomic per (slot, feature chunk) are what
+// bound the kernel above (REDG issue rate, ~0.9 TB/s of atomic traffic on the chip).  Per SOURCE row j the same gradient is
+//   grad_gathered[j] = sum_{i <- j} (c0_i + c1_i * bias_i)  +  gathered[j] * sum_{i <- j} c1_i  +  routed min / max terms,
+// so this entry point stops after the coefficients: it writes the row [c0' | c1] per destination, routes min / max with ONE
+// scalar atomic per (row, feature) and writes grad_row_bias in closed form (deg * c0 + c1 * sum_m + gmin + gmax).  The two
+// sums over the out-edges are a 'sum' aggregation of those rows over the transposed graph (pna_aggregate_fwd, no atomics),
+// folded into grad_gathered by pna_aggregate_bwd_combine.
 #include "pna_aggregate.cuh"
 #include <string.h>
 
@@ -21,6 +29,8 @@ struct BParams {
   float* gg; long long ldgg;          // grad_gathered [n_src, F] fp32, accumulated
   float* gb; long long ldgb;          // grad_row_bias [n_rows, F] fp32, written (nullable)
   int vec_atomics;                    // grad_gathered rows are 16-byte aligned
+  float* coef; long long ldc;         // coefficient mode (pna_aggregate_bwd_coef): [n_rows, ldc] rows [c0' | c1], c1 at column coef_c1
+  int coef_c1, coef_vec;
 };
 
 template <int VEC>
@@ -142,6 +152,43 @@ __device__ __forceinline__ LaneCols lane_cols(const KParams& p, int gl, int fblo
   return c;
 }
 
+// coefficient mode: what one destination row hands to its sources.  c0' = c0 + c1 * bias; min / max go to the source of the
+// one slot that attained them (st.amn / st.amx: absolute CSR slots, -1 = none); grad_row_bias in closed form.
+template <int VEC>
+__device__ __forceinline__ void emit_row(const BParams& b, long long row, int deg, const LaneCols& lc, const Stats<VEC>& st,
+                                         const Coef<VEC>& c, const float (&bias)[VEC], bool has_bias) {
+  const KParams& p = b.k;
+  float* crow = b.coef + row * b.ldc + lc.f;
+  float c0p[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) c0p[i] = has_bias ? fmaf(c.c1[i], bias[i], c.c0[i]) : c.c0[i];
+  bool stored = false;
+  if constexpr (VEC % 4 == 0) {
+    if (b.coef_vec) {     // 16-byte aligned rows and halves
+#pragma unroll
+      for (int i = 0; i < VEC; i += 4) {
+        *reinterpret_cast<float4*>(crow + i) = make_float4(c0p[i], c0p[i + 1], c0p[i + 2], c0p[i + 3]);
+        *reinterpret_cast<float4*>(crow + b.coef_c1 + i) = make_float4(c.c1[i], c.c1[i + 1], c.c1[i + 2], c.c1[i + 3]);
+      }
+      stored = true;
+    }
+  }
+  if (!stored) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { crow[i] = c0p[i]; crow[b.coef_c1 + i] = c.c1[i]; }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    if (c.gmin[i] != 0.f && st.amn[i] >= 0) atomicAdd(b.gg + (long long)__ldg(p.col + st.amn[i]) * b.ldgg + lc.f + i, c.gmin[i]);
+    if (c.gmax[i] != 0.f && st.amx[i] >= 0) atomicAdd(b.gg + (long long)__ldg(p.col + st.amx[i]) * b.ldgg + lc.f + i, c.gmax[i]);
+  }
+  if (b.gb) {
+    const float degf = (float)deg;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) b.gb[row * b.ldgb + lc.f + i] = degf * c.c0[i] + c.c1[i] * st.sum[i] + c.gmin[i] + c.gmax[i];
+  }
+}
+
 constexpr int kBwdThreads = 256;
 
 // ---- rows below the split threshold: one lane group per row --------------------------------------------------------
@@ -194,6 +241,10 @@ __global__ void __launch_bounds__(kBwdThreads) k_bwd_rows(const BParams b) {
   }
   Coef<VEC> c;
   coefficients<T, VEC>(b, row, deg, lc.ooff, st, c);
+  if (b.coef) {   // coefficient mode: no second pass over the slots
+    emit_row<VEC>(b, row, deg, lc, st, c, bias, has_bias);
+    return;
+  }
   float gbs[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) gbs[i] = 0.f;
@@ -303,6 +354,15 @@ __global__ void __launch_bounds__(kBwdThreads) k_bwd_hub_coef(const BParams b) {
   }
   Coef<VEC> c;
   coefficients<T, VEC>(b, row, deg, lc.ooff, st, c);
+  if (b.coef) {   // coefficient mode: the split row ends here, like every other row
+    const bool has_bias = p.bias != nullptr;
+    float bias[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) bias[i] = 0.f;
+    if (has_bias) Io<T, VEC>::load(static_cast<const T*>(p.bias) + row * p.ldb + lc.f, bias);
+    emit_row<VEC>(b, row, deg, lc, st, c, bias, has_bias);
+    return;
+  }
   float* co = p.partials + (p.n_chunks + h) * 6ll * p.F + lc.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -387,8 +447,10 @@ static int launch_bwd(const BParams& b, cudaStream_t st) {
     PNA_CUDA_TRY(cudaGetLastError());
     k_bwd_hub_coef<T, VEC, G><<<dim3((unsigned)gh, gy), kBwdThreads, 0, st>>>(b);
     PNA_CUDA_TRY(cudaGetLastError());
-    k_bwd_hub_scatter<T, VEC, G><<<dim3((unsigned)gc, gy), kBwdThreads, 0, st>>>(b);
-    PNA_CUDA_TRY(cudaGetLastError());
+    if (!b.coef) {
+      k_bwd_hub_scatter<T, VEC, G><<<dim3((unsigned)gc, gy), kBwdThreads, 0, st>>>(b);
+      PNA_CUDA_TRY(cudaGetLastError());
+    }
   }
   return PNA_OK;
 }
@@ -406,12 +468,30 @@ static int launch_bwd_typed(const BParams& b, cudaStream_t st) {
 
 static bool al16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
 
+// ---- phase 3 of the coefficient path: grad_gathered[j] += S0[j] + gathered[j] * S1[j] ------------------------------------
+// sums[j] = [S0 | S1] (S1 at column c1): the 'sum' of the coefficient rows over the out-edges of source row j.
+template <typename T>
+__global__ void __launch_bounds__(256) k_bwd_combine(const float* __restrict__ sums, long long lds, int c1, const T* __restrict__ x,
+                                                     long long ldx, float* __restrict__ gg, long long ldgg, long long n_src, int F) {
+  const long long total = n_src * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / F;
+    const int f = (int)(i - r * F);
+    const float s0 = sums[r * lds + f], s1 = sums[r * lds + c1 + f];
+    float xv;
+    if constexpr (sizeof(T) == 4) xv = x[r * ldx + f];
+    else xv = __bfloat162float(x[r * ldx + f]);
+    gg[r * ldgg + f] += s0 + xv * s1;
+  }
+}
+
 }  // namespace pna
 
 using namespace pna;
 
-extern "C" int pna_aggregate_bwd(const pna_agg_t* d, const void* grad_out, int64_t ld_grad_out, float* grad_gathered,
-                                 int64_t ld_grad_gathered, float* grad_row_bias, int64_t ld_grad_row_bias, pna_stream_t stream) {
+static int bwd_entry(const pna_agg_t* d, const void* grad_out, int64_t ld_grad_out, float* grad_gathered, int64_t ld_grad_gathered,
+                     float* grad_row_bias, int64_t ld_grad_row_bias, float* coef, int64_t ld_coef, int32_t coef_c1,
+                     pna_stream_t stream) {
   PNA_REQUIRE(d != nullptr, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: null descriptor");
   PNA_REQUIRE(d->n_rows >= 0 && d->n_feat > 0 && d->n_towers > 0 && d->n_feat % d->n_towers == 0, PNA_ERR_BAD_ARG,
               "pna_aggregate_bwd: bad sizes");
@@ -448,6 +528,13 @@ extern "C" int pna_aggregate_bwd(const pna_agg_t* d, const void* grad_out, int64
   b.gb = grad_row_bias; b.ldgb = ld_grad_row_bias;
   PNA_REQUIRE(b.ldgo >= (long long)p.T * p.Wt, PNA_ERR_BAD_ARG, "pna_aggregate_bwd: ld_grad_out too small");
   b.vec_atomics = al16(grad_gathered) && (ld_grad_gathered % 4 == 0);
+  if (coef) {
+    PNA_REQUIRE(d->col != nullptr, PNA_ERR_UNSUPPORTED, "pna_aggregate_bwd_coef: per-edge messages (col == NULL) have no shared sources");
+    PNA_REQUIRE(coef_c1 >= p.F && ld_coef >= (long long)coef_c1 + p.F, PNA_ERR_BAD_ARG,
+                "pna_aggregate_bwd_coef: coefficient rows need c1_column >= n_feat and ld_coef >= c1_column + n_feat");
+    b.coef = coef; b.ldc = ld_coef; b.coef_c1 = coef_c1;
+    b.coef_vec = al16(coef) && (ld_coef % 4 == 0) && (coef_c1 % 4 == 0);
+  }
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int esz = d->dtype == PNA_F32 ? 4 : 2;
@@ -456,4 +543,41 @@ extern "C" int pna_aggregate_bwd(const pna_agg_t* d, const void* grad_out, int64
   if (p.bias) vec_ok = vec_ok && al16(p.bias) && (p.ldb % vec == 0);
   if (d->dtype == PNA_F32) return vec_ok ? launch_bwd_typed<float, 4>(b, st) : launch_bwd_typed<float, 1>(b, st);
   return vec_ok ? launch_bwd_typed<__nv_bfloat16, 8>(b, st) : launch_bwd_typed<__nv_bfloat16, 1>(b, st);
+}
+
+extern "C" int pna_aggregate_bwd(const pna_agg_t* d, const void* grad_out, int64_t ld_grad_out, float* grad_gathered,
+                                 int64_t ld_grad_gathered, float* grad_row_bias, int64_t ld_grad_row_bias, pna_stream_t stream) {
+  return bwd_entry(d, grad_out, ld_grad_out, grad_gathered, ld_grad_gathered, grad_row_bias, ld_grad_row_bias, nullptr, 0, 0, stream);
+}
+
+extern "C" int pna_aggregate_bwd_coef(const pna_agg_t* d, const void* grad_out, int64_t ld_grad_out, float* coef, int64_t ld_coef,
+                                      int32_t c1_column, float* grad_gathered, int64_t ld_grad_gathered, float* grad_row_bias,
+                                      int64_t ld_grad_row_bias, pna_stream_t stream) {
+  PNA_REQUIRE(coef != nullptr, PNA_ERR_BAD_ARG, "pna_aggregate_bwd_coef: null coefficient buffer");
+  return bwd_entry(d, grad_out, ld_grad_out, grad_gathered, ld_grad_gathered, grad_row_bias, ld_grad_row_bias, coef, ld_coef,
+                   c1_column, stream);
+}
+
+extern "C" int pna_aggregate_bwd_combine(const float* coef_sums, int64_t ld_sums, int32_t c1_column, const void* gathered,
+                                         int64_t ld_gathered, int32_t dtype, float* grad_gathered, int64_t ld_grad_gathered,
+                                         int64_t n_src, int32_t n_feat, pna_stream_t stream) {
+  PNA_REQUIRE(n_src >= 0 && n_feat > 0 && c1_column >= n_feat, PNA_ERR_BAD_ARG, "pna_aggregate_bwd_combine: bad sizes");
+  PNA_REQUIRE(dtype == PNA_F32 || dtype == PNA_BF16, PNA_ERR_UNSUPPORTED, "pna_aggregate_bwd_combine: dtype %d", dtype);
+  if (n_src == 0) return PNA_OK;
+  PNA_REQUIRE(coef_sums && gathered && grad_gathered, PNA_ERR_BAD_ARG, "pna_aggregate_bwd_combine: null pointer");
+  PNA_REQUIRE(ld_sums >= (long long)c1_column + n_feat && ld_gathered >= n_feat && ld_grad_gathered >= n_feat, PNA_ERR_BAD_ARG,
+              "pna_aggregate_bwd_combine: row pitch too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = n_src * (long long)n_feat;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;      // grid-stride: 16 CTAs of 256 threads per SM
+  if (dtype == PNA_F32)
+    k_bwd_combine<float><<<(unsigned)blocks, 256, 0, st>>>(coef_sums, ld_sums, c1_column, static_cast<const float*>(gathered),
+                                                           ld_gathered, grad_gathered, ld_grad_gathered, n_src, n_feat);
+  else
+    k_bwd_combine<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(coef_sums, ld_sums, c1_column,
+                                                                   static_cast<const __nv_bfloat16*>(gathered), ld_gathered,
+                                                                   grad_gathered, ld_grad_gathered, n_src, n_feat);
+  PNA_CUDA_TRY(cudaGetLastError());
+  return PNA_OK;
 }

@@ -29,6 +29,7 @@ def batch_csr(batch: torch.Tensor, n_graphs: int) -> CSRGraph:
         return hit[1]
     n = int(batch.numel())
     csr = build_csr(torch.arange(n, device=batch.device), batch, n_graphs, n_src=n)
+    csr.sources_unique = True       # one out-edge per node: the backward keeps its one-call path (aggregate.aggregate_backward)
     _CACHE[key] = (batch, csr)
     while len(_CACHE) > 8:
         _CACHE.popitem(last=False)

@@ -23,7 +23,7 @@ def declared_functions():
 def test_library_is_built_and_loads():
     assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build()"
     L = _lib.lib()
-    assert L.pna_query(_lib.QUERY_ABI_VERSION) == _lib.ABI_VERSION == 7
+    assert L.pna_query(_lib.QUERY_ABI_VERSION) == _lib.ABI_VERSION == 8
     assert L.pna_query(_lib.QUERY_SM_ARCH) == 100
 
 
