@@ -249,8 +249,13 @@ def _round_up(n: int, m: int) -> int:
 
 
 def backward_mode() -> str:
-    """PNA_B200_BWD=atomic keeps the one-call backward (a vector atomic per edge and feature chunk); default "coef"."""
-    return "atomic" if os.environ.get("PNA_B200_BWD", "coef") == "atomic" else "coef"
+    """Which backward runs for gathered rows: "atomic" (default) = ``pna_aggregate_bwd``, one call, a vector atomic per edge and
+    feature chunk; ``PNA_B200_BWD=coef`` = per-destination coefficient rows (``pna_aggregate_bwd_coef``), their sums over the
+    transposed graph through the forward kernels, ``pna_aggregate_bwd_combine`` -- atomics only for min / max.  Measured
+    (profiles/r02_backward_ab.json): config 2 1.12 ms atomic vs 1.30 ms coef; config-5 share (hot source rows) 50.2 vs 26.6 ms,
+    but regrouping sum_i (c0_i + c1_i x_j) into sum_i c0_i + x_j sum_i c1_i cancels badly where many rows have var ~ 0
+    (2.6x the fp32 error of the per-edge evaluation on a power-law multigraph), so it stays opt-in."""
+    return "coef" if os.environ.get("PNA_B200_BWD", "atomic") == "coef" else "atomic"
 
 
 class _PNAAggregate(torch.autograd.Function):

@@ -391,7 +391,9 @@ def test_config2_size_independent_properties(P, O, arxiv):
 
 
 # ---- autograd through the drop-in layer --------------------------------------------------------------------------
-def test_backward_matches_reference_autograd(P, O):
+@pytest.mark.parametrize("bwd_mode", ["atomic", "coef"])
+def test_backward_matches_reference_autograd(P, O, bwd_mode, monkeypatch):
+    monkeypatch.setenv("PNA_B200_BWD", bwd_mode)        # one-call backward | coefficient rows + sum over the transposed graph
     n, e, f = 120, 900, 16
     ei = rand_graph(n, e, seed=31, hub=400)
     x = torch.randn(n, f)
@@ -469,8 +471,10 @@ def test_golden_dense_layer(P, name):
 
 
 # ---- backward kernel (pna_aggregate_bwd) against the reference's autograd (CPU oracle) ---------------------------
+@pytest.mark.parametrize("bwd_mode", ["atomic", "coef"])
 @pytest.mark.parametrize("name", ["pyg_conv_t1", "pyg_conv_t4_div", "pyg_conv_t5_rep", "pyg_conv_edge", "pyg_conv_pre2"])
-def test_backward_full_conv_matches_reference_autograd(P, O, name):
+def test_backward_full_conv_matches_reference_autograd(P, O, name, bwd_mode, monkeypatch):
+    monkeypatch.setenv("PNA_B200_BWD", bwd_mode)
     g = load_golden(name)
     c = g["ctor"]
     kw = dict(edge_dim=c["edge_dim"], towers=c["towers"], pre_layers=c["pre_layers"], post_layers=c["post_layers"],
@@ -495,7 +499,9 @@ def test_backward_full_conv_matches_reference_autograd(P, O, name):
         assert err < 2e-3, f"{n1}: relative Frobenius error {err:.2e}"
 
 
-def test_backward_all_aggregators_with_split_rows_and_ties(P, O):
+@pytest.mark.parametrize("bwd_mode", ["atomic", "coef"])
+def test_backward_all_aggregators_with_split_rows_and_ties(P, O, bwd_mode, monkeypatch):
+    monkeypatch.setenv("PNA_B200_BWD", bwd_mode)
     n, e, f = 150, 1200, 12
     ei = rand_graph(n, e, seed=77, hub=700)
     g = torch.Generator().manual_seed(3)
@@ -538,7 +544,9 @@ def test_backward_all_aggregators_with_split_rows_and_ties(P, O):
     torch.testing.assert_close(xm3.grad.cpu(), want, rtol=0, atol=1e-6)
 
 
-def test_backward_bf16_runs_and_is_close(P, O):
+@pytest.mark.parametrize("bwd_mode", ["atomic", "coef"])
+def test_backward_bf16_runs_and_is_close(P, O, bwd_mode, monkeypatch):
+    monkeypatch.setenv("PNA_B200_BWD", bwd_mode)
     n, e, f = 200, 1500, 64
     ei = rand_graph(n, e, seed=9)
     x = torch.randn(n, f, generator=torch.Generator().manual_seed(4)).to(torch.bfloat16)
