@@ -173,3 +173,34 @@ def test_emulated_backward_bf16_rows(emu):
     want_x, _ = reference_grads(x.float(), None, src, dst, n, w.float(), aggrs, scalers, avg)
     torch.testing.assert_close(gg1, want_x, rtol=1e-3, atol=5e-4)
     torch.testing.assert_close(gg2, want_x, rtol=1e-3, atol=5e-4)
+
+
+def test_emulated_backward_random_shapes(emu):
+    """Both paths over random widths, tower counts, aggregator / scaler subsets, with and without row_bias, graphs with and
+    without split rows: every launch geometry of launch_bwd_typed (G = 1 ... 32 lanes per row, vector and scalar rows)."""
+    import random
+    rnd = random.Random(0)
+    for it in range(80):
+        towers = rnd.choice([1, 1, 1, 2, 3, 5])
+        f = rnd.choice([1, 2, 3, 4, 5, 7, 8, 12, 15, 16, 20, 33]) * towers
+        n, e = rnd.randint(3, 70), rnd.randint(1, 500)
+        g = torch.Generator().manual_seed(it)
+        src = torch.randint(0, n, (e,), generator=g)
+        dst = torch.randint(0, max(1, n - rnd.randint(0, 3)), (e,), generator=g)
+        if e > 100 and rnd.random() < 0.5:
+            dst[:rnd.randint(SPLIT, min(e, 200))] = rnd.randint(0, n - 1)
+        x = torch.randn(n, f, generator=g)
+        bias = torch.randn(n, f, generator=g) if rnd.random() < 0.5 else None
+        aggrs, scalers = rnd.sample(AGGRS, rnd.randint(1, 6)), rnd.sample(SCALERS, rnd.randint(1, 5))
+        avg = O.avg_deg_from_histogram(torch.bincount(torch.bincount(dst, minlength=n)))
+        w = torch.randn(n, len(aggrs) * len(scalers) * f, generator=g)
+        (gg1, gb1), (gg2, gb2) = run_both(emu, x, bias, src, dst, n, w, aggrs, scalers, avg, towers)
+        want_x, want_b = reference_grads(x, bias, src, dst, n, w, aggrs, scalers, avg, towers)
+        what = f"case {it}: F={f} towers={towers} N={n} E={e} {aggrs} {scalers} bias={bias is not None}"
+        for got in (gg1, gg2):
+            torch.testing.assert_close(got, want_x, rtol=2e-3, atol=2e-3, msg=lambda m: f"{what}\n{m}")
+        if bias is not None:
+            has_in = torch.bincount(dst, minlength=n) > 0
+            for got in (gb1, gb2):
+                torch.testing.assert_close(got[has_in], want_b[has_in], rtol=2e-3, atol=5e-3, msg=lambda m: f"{what}\n{m}")
+                assert torch.equal(got[~has_in], torch.zeros_like(got[~has_in]))
