@@ -1,6 +1,7 @@
-"""Build tests/emu/_build/libpna_bwd_emu.so: pna_b200/csrc/pna_aggregate_bwd.cu with every kernel launch rewritten into a
-sequential host loop (cuda_host_shim.h), compiled by g++.  Test infrastructure for the CPU suite: the backward kernels have
-no intra-block communication, so running their threads one after the other checks index arithmetic and control flow."""
+"""Build tests/emu/_build/lib<name>_emu.so: one pna_b200/csrc/*.cu with every kernel launch rewritten into a sequential host
+loop (cuda_host_shim.h), compiled by g++.  Test infrastructure for the CPU suite: kernels without intra-block communication
+(the backward, the halo pull) can be run thread after thread, which checks their index arithmetic and control flow.  Inline
+PTX (only in kernels that are not emulated, e.g. the flag barrier) is replaced by a call that aborts."""
 import os
 import re
 import subprocess
@@ -8,9 +9,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SRC = os.path.join(ROOT, "pna_b200", "csrc", "pna_aggregate_bwd.cu")
+CSRC = os.path.join(ROOT, "pna_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
-LIB = os.path.join(BUILD, "libpna_bwd_emu.so")
 
 
 def _split_top_level(s: str):
@@ -52,16 +52,36 @@ def rewrite_launches(text: str) -> str:
         pos = k + 1
 
 
-def build(force: bool = False) -> str:
+def strip_inline_ptx(text: str) -> str:
+    """`asm [volatile](...);` statements -> emu_unsupported(): the kernels that contain them are not emulated."""
+    out, pos = "", 0
+    for m in re.finditer(r"\basm\s*(volatile\s*)?\(", text):
+        if m.start() < pos:
+            continue
+        depth, k = 0, m.end() - 1
+        while True:
+            depth += text[k] == "("
+            depth -= text[k] == ")"
+            if depth == 0:
+                break
+            k += 1
+        out += text[pos:m.start()] + "emu_unsupported()"
+        pos = k + 1
+    return out + text[pos:]
+
+
+def build(source: str = "pna_aggregate_bwd.cu", force: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
-    deps = [SRC, os.path.join(HERE, "cuda_host_shim.h"), __file__,
-            os.path.join(ROOT, "pna_b200", "csrc", "pna_aggregate.cuh"), os.path.join(ROOT, "pna_b200", "csrc", "common.cuh"),
-            os.path.join(ROOT, "include", "pna_b200.h")]
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
-        return LIB
-    body = rewrite_launches(open(SRC).read())
-    body = body.replace('#include "pna_aggregate.cuh"', f'#include "{ROOT}/pna_b200/csrc/pna_aggregate.cuh"')
-    tu = os.path.join(BUILD, "pna_aggregate_bwd_emu.cpp")
+    src = os.path.join(CSRC, source)
+    stem = os.path.splitext(source)[0]
+    lib = os.path.join(BUILD, f"lib{stem}_emu.so")
+    deps = [src, os.path.join(HERE, "cuda_host_shim.h"), __file__, os.path.join(CSRC, "pna_aggregate.cuh"),
+            os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "pna_b200.h")]
+    if not force and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps):
+        return lib
+    body = strip_inline_ptx(rewrite_launches(open(src).read()))
+    body = re.sub(r'#include "(pna_aggregate\.cuh|common\.cuh)"', lambda m: f'#include "{CSRC}/{m.group(1)}"', body)
+    tu = os.path.join(BUILD, f"{stem}_emu.cpp")
     with open(tu, "w") as f:
         f.write(f'#include "{HERE}/cuda_host_shim.h"\n')
         f.write(body)
@@ -75,10 +95,12 @@ int cuda_fail(cudaError_t, const char* what) { set_error("%s", what); return PNA
 extern "C" const char* emu_last_error(void) { return pna::g_err; }
 """)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w", f"-I{cuda_inc}", tu, "-o", LIB]
+    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w", f"-I{cuda_inc}", tu, "-o", lib]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["pna_aggregate_bwd.cu"]
+    for name in names:
+        print(build(name, force="--force" in sys.argv))

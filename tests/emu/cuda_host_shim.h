@@ -46,8 +46,15 @@ static void emu_launch(F body, dim3 grid, dim3 block) {
 #define EMU_LAUNCH(kern, grid, block, ...) emu_launch([&]() { kern(__VA_ARGS__); }, dim3(grid), dim3(block))
 
 #define cudaGetLastError() cudaSuccess
+#define cudaGetDevice(p) (*(p) = 0, cudaSuccess)
+#define cudaDeviceGetAttribute(p, attr, dev) (*(p) = 2, cudaSuccess)     /* "2 SMs": small grids, grid-stride loops get exercised */
+#include <stdlib.h>
+static inline void emu_unsupported() { abort(); }                        /* inline PTX: that kernel is not emulated */
+static inline void __threadfence_system() {}
+static inline void __nanosleep(unsigned) {}
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 template <class T> static inline void __stwt(T* p, T v) { *p = v; }
@@ -70,4 +77,5 @@ static inline float4 atomicAdd(float4* p, float4 v) {
 }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
+static inline int atomicExch(int* p, int v) { const int o = *p; *p = v; return o; }
 static inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }

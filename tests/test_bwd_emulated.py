@@ -27,7 +27,7 @@ def emu():
     build_emu = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(build_emu)
     try:
-        L = C.CDLL(build_emu.build())
+        L = C.CDLL(build_emu.build("pna_aggregate_bwd.cu"))
     except Exception as exc:            # no CUDA headers on this machine
         pytest.skip(f"emulation library did not build: {exc}")
     L.emu_last_error.restype = C.c_char_p
