@@ -1,7 +1,12 @@
 """Build tests/emu/_build/lib<name>_emu.so: one pna_b200/csrc/*.cu with every kernel launch rewritten into a sequential host
 loop (cuda_host_shim.h), compiled by g++.  Test infrastructure for the CPU suite: kernels without intra-block communication
 (the backward, the halo pull) can be run thread after thread, which checks their index arithmetic and control flow.  Inline
-PTX (only in kernels that are not emulated, e.g. the flag barrier) is replaced by a call that aborts."""
+PTX (only in kernels that are not emulated, e.g. the flag barrier) is replaced by a call that aborts.
+
+Memory checking (a host-side stand-in for compute-sanitizer): set PNA_EMU_ASAN=1 and preload the sanitizer runtime,
+    PNA_EMU_ASAN=1 ASAN_OPTIONS=detect_leaks=0 LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
+        python -m pytest tests/test_bwd_emulated.py tests/test_pull_emulated.py -q
+then every access of the emulated kernels into the torch-allocated buffers is bounds-checked (round 2: clean)."""
 import os
 import re
 import subprocess
@@ -70,11 +75,12 @@ def strip_inline_ptx(text: str) -> str:
     return out + text[pos:]
 
 
-def build(source: str = "pna_aggregate_bwd.cu", force: bool = False) -> str:
+def build(source: str = "pna_aggregate_bwd.cu", force: bool = False, asan: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
+    asan = asan or os.environ.get("PNA_EMU_ASAN") == "1"
     src = os.path.join(CSRC, source)
     stem = os.path.splitext(source)[0]
-    lib = os.path.join(BUILD, f"lib{stem}_emu.so")
+    lib = os.path.join(BUILD, f"lib{stem}_emu{'_asan' if asan else ''}.so")
     deps = [src, os.path.join(HERE, "cuda_host_shim.h"), __file__, os.path.join(CSRC, "pna_aggregate.cuh"),
             os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "pna_b200.h")]
     if not force and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps):
@@ -96,6 +102,8 @@ extern "C" const char* emu_last_error(void) { return pna::g_err; }
 """)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w", f"-I{cuda_inc}", tu, "-o", lib]
+    if asan:      # out-of-bounds accesses of the kernels into the (torch-allocated) buffers: see the module docstring
+        cmd[1:1] = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
     subprocess.run(cmd, check=True)
     return lib
 
